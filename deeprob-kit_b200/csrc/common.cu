@@ -1,0 +1,99 @@
+// common.cu -- error reporting and cached device attributes.
+#include "common.cuh"
+
+namespace dpk {
+
+static thread_local char g_error[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct DevAttr { int sms; int smem; bool ok; };
+static DevAttr g_attr[64];
+
+static DevAttr& attr() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  DevAttr& a = g_attr[dev];
+  if (!a.ok) {
+    int sms = 0, smem = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    a.sms = sms > 0 ? sms : 148;
+    a.smem = smem > 0 ? smem : 48 * 1024;
+    a.ok = true;  // benign race: every thread writes the same values
+  }
+  return a;
+}
+
+// ---- profiling -------------------------------------------------------------------------------
+}  // namespace dpk
+#include <atomic>
+#include <mutex>
+#include <vector>
+namespace dpk {
+struct ProfRec { int cat; cudaEvent_t a, b; };
+static std::atomic<long long> g_launches[CAT_COUNT];
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec*> g_prof_recs;
+
+ProfScope::ProfScope(int cat, cudaStream_t st, int launches) : cat_(cat), st_(st), rec_(nullptr) {
+  g_launches[cat].fetch_add(launches, std::memory_order_relaxed);
+  if (g_prof_on.load(std::memory_order_relaxed)) {
+    ProfRec* r = new ProfRec{cat, nullptr, nullptr};
+    if (cudaEventCreate(&r->a) == cudaSuccess && cudaEventCreate(&r->b) == cudaSuccess) {
+      cudaEventRecord(r->a, st);
+      rec_ = r;
+    } else {
+      delete r;
+    }
+  }
+}
+ProfScope::~ProfScope() {
+  if (rec_) {
+    ProfRec* r = static_cast<ProfRec*>(rec_);
+    cudaEventRecord(r->b, st_);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+  }
+}
+
+int sm_count() { return attr().sms; }
+int max_dynamic_smem() { return attr().smem; }
+
+}  // namespace dpk
+
+extern "C" int dpk_abi_version(void) { return DPK_ABI_VERSION; }
+extern "C" const char* dpk_last_error(void) { return dpk::g_error; }
+
+// enable/disable CUDA-event bracketing of every kernel category (off by default: zero overhead)
+extern "C" int dpk_profile_enable(int on) { dpk::g_prof_on.store(on ? 1 : 0); return DPK_OK; }
+
+// Sum of elapsed milliseconds and number of kernel launches per category since the last read
+// (arrays of `ncat` entries, see ProfCat in csrc/common.cuh); synchronises the recorded events.
+extern "C" int dpk_profile_read(double* ms, int64_t* launches, int32_t ncat) {
+  using namespace dpk;
+  for (int c = 0; c < ncat; ++c) {
+    if (ms) ms[c] = 0.0;
+    if (launches) launches[c] = (c < CAT_COUNT) ? g_launches[c].exchange(0) : 0;
+  }
+  std::vector<ProfRec*> recs;
+  { std::lock_guard<std::mutex> lk(g_prof_mu); recs.swap(g_prof_recs); }
+  int rc = DPK_OK;
+  for (ProfRec* r : recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r->b) != cudaSuccess || cudaEventElapsedTime(&t, r->a, r->b) != cudaSuccess)
+      rc = set_error(DPK_E_CUDA, "profile event read failed");
+    else if (ms && r->cat < ncat) ms[r->cat] += t;
+    cudaEventDestroy(r->a); cudaEventDestroy(r->b);
+    delete r;
+  }
+  return rc;
+}

@@ -1,0 +1,670 @@
+// ratspn_fwd.cu -- RAT-SPN log-likelihood forward (one kernel per region-graph level).
+//
+// Reference path being replaced (deeprob-kit, paths relative to /root/reference):
+//   RegionGraphLayer.forward  deeprob/spn/layers/ratspn.py:87-108   gather + leaf LL + NaN->0 + pad + sum
+//   ProductLayer.forward      deeprob/spn/layers/ratspn.py:272-286  outer sum of sibling regions
+//   SumLayer.forward          deeprob/spn/layers/ratspn.py:363-378  logsumexp(x + log_softmax(W))
+//   RootLayer.forward         deeprob/spn/layers/ratspn.py:446-458
+// The reference materialises (B,G0,K,dim) and (B,P,O,K^2); here
+//   * the leaf kernel stages a transposed x tile in shared memory once and sweeps every region over
+//     it with 2 FMA per (feature, channel):  t = x/sigma - mu/sigma ; acc += t*t
+//   * product+sum are fused ("einsum" form):
+//       y[b,p,o] = ml + mr + log sum_ij softmax(W)[p,o,ij] * exp(l_i - ml) * exp(r_j - mr)
+//     (2K exps instead of O*K^2), with an exact log-domain fallback when the linear-domain sum
+//     underflows, so the result matches the reference's logsumexp even for extreme weights.
+#include <algorithm>
+
+#include "ratspn_plan.cuh"
+
+namespace dpk {
+
+// =================================================================================================
+// Parameter preparation (tiny; re-run every call because the optimiser updates parameters in place)
+// =================================================================================================
+template <int KIND>
+__global__ void ratspn_prep_leaf_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                        const int32_t* __restrict__ region_len, int G0, int K, int dim,
+                                        int KC, int nKc, float* __restrict__ tab, float* __restrict__ cd) {
+  const int Kp = KC * nKc;
+  const int64_t total = (int64_t)G0 * Kp * dim;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % dim);
+    const int kk = (int)((idx / dim) % Kp);
+    const int g = (int)(idx / ((int64_t)dim * Kp));
+    const int c = kk / KC, k = kk % KC;
+    const bool live = kk < K && d < region_len[g];
+    const size_t src = ((size_t)g * K + kk) * dim + d;
+    const size_t row = ((size_t)g * nKc + c) * dim + d;
+    if (KIND == DPK_LEAF_GAUSSIAN) {
+      float rs = 0.f, mr = 0.f, cdv = 0.f;
+      if (live) {
+        const float sigma = p1[src], mu = p0[src];
+        rs = 1.0f / sigma;
+        mr = -mu * rs;
+        cdv = -logf(sigma) - kLogSqrt2Pi;
+      }
+      tab[row * 2 * KC + k] = rs;
+      tab[row * 2 * KC + KC + k] = mr;
+      cd[row * KC + k] = cdv;
+    } else {
+      float lg = 0.f, cdv = 0.f;
+      if (live) {
+        lg = p0[src];
+        cdv = -(fmaxf(lg, 0.f) + log1pf(expf(-fabsf(lg))));  // -softplus(logit)
+      }
+      tab[row * KC + k] = lg;
+      cd[row * KC + k] = cdv;
+    }
+  }
+}
+
+__global__ void ratspn_prep_const_kernel(const float* __restrict__ cd, const int32_t* __restrict__ region_len,
+                                         int G0, int dim, int KC, int nKc, float* __restrict__ cst) {
+  const int Kp = KC * nKc;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G0 * Kp) return;
+  const int g = idx / Kp, kk = idx % Kp, c = kk / KC, k = kk % KC;
+  const int len = region_len[g];
+  float s = 0.f;
+  for (int d = 0; d < len; ++d) s += cd[(((size_t)g * nKc + c) * dim + d) * KC + k];
+  cst[idx] = s;
+}
+
+// Row-wise softmax / log-softmax of raw mixture logits, scattered into the chunked layouts.
+//   mode 0 (inner sum level): src (P, O, Kin2); row = (p, o);     dst [p][o/OC][ij][o%OC]
+//   mode 1 (root):            src (C, P*Kin2); row = c;           dst [p][c/OC][ij][c%OC]
+// One CTA per (padded) row; padded rows (o >= O) are written as weight 0 / log-weight -inf.
+__global__ void ratspn_prep_weight_kernel(const float* __restrict__ src, int mode, int P, int O, int Kin2,
+                                          int OC, int nOc, float* __restrict__ wsoft, float* __restrict__ wlog) {
+  __shared__ float red[32];
+  const int Op = OC * nOc;
+  int p_row, o;
+  int64_t len;
+  const float* row;
+  if (mode == 0) { p_row = blockIdx.x / Op; o = blockIdx.x % Op; len = Kin2; row = src + ((size_t)p_row * O + o) * Kin2; }
+  else           { p_row = 0;               o = blockIdx.x;      len = (int64_t)P * Kin2; row = src + (size_t)o * len; }
+  const bool live = o < O;
+  float lse = 0.f;
+  if (live) {
+    float m = -INFINITY;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) m = fmaxf(m, row[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+    m = warp_max(m);
+    m = __shfl_sync(0xffffffffu, m, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) red[0] = m;
+    __syncthreads();
+    m = red[0];
+    __syncthreads();
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += expf(row[i] - m);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    __syncthreads();
+    if (threadIdx.x == 0) red[0] = m + logf(s);
+    __syncthreads();
+    lse = red[0];
+  }
+  const int oc = o / OC, ok = o % OC;
+  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+    const int p = (mode == 0) ? p_row : (int)(i / Kin2);
+    const int ij = (mode == 0) ? (int)i : (int)(i % Kin2);
+    const size_t dst = (((size_t)p * nOc + oc) * Kin2 + ij) * OC + ok;
+    const float lw = live ? row[i] - lse : -INFINITY;
+    wlog[dst] = lw;
+    wsoft[dst] = live ? expf(lw) : 0.f;
+  }
+}
+
+// =================================================================================================
+// Leaf level
+// =================================================================================================
+struct LeafArgs {
+  const float* x;            // (B, D)
+  const int32_t* mask;       // (G0, dim)
+  const int32_t* region_len; // (G0)
+  const float* tab;          // [G0][nKc][dim][NP*KC]
+  const float* cd;           // [G0][nKc][dim][KC]
+  const float* cst;          // [G0][Kp]
+  float* out;                // [G0][K][Bp]
+  int64_t B, Bp;
+  int D, G0, K, dim, nKc, regions_per_cta;
+};
+
+// One CTA = one tile of TB = 32*ST samples x a contiguous range of regions.  8 warps; a warp owns a
+// region at a time, lanes = samples, so the per-(region,dim) parameters are warp-uniform broadcast
+// loads and the x reads from the transposed tile are bank-conflict free.
+// Shared tile layout: element (feature f, sample s) at f*TB + ((s&31) ^ (f&31)) + (s & ~31):
+// conflict-free both for the transposing fill (lanes = features) and for the sweep (lanes = samples).
+template <int KC, int ST, int KIND, bool STAGE>
+__global__ void __launch_bounds__(256) ratspn_leaf_kernel(const LeafArgs a) {
+  extern __shared__ __align__(16) float xs[];
+  constexpr int TB = 32 * ST;
+  constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;
+  constexpr int ROW = NP * KC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b0 = (int64_t)blockIdx.x * TB;
+
+  int any_nonfinite = 1;  // unstaged variant: always take the exact nan_to_num path
+  if constexpr (STAGE) {
+    bool bad = false;
+    for (int s = warp; s < TB; s += 8) {
+      const int64_t b = b0 + s;
+      const bool inb = b < a.B;
+      const float* row = a.x + b * a.D;
+      const int sw = s & 31, hi = s & ~31;
+#pragma unroll 4
+      for (int f = lane; f < a.D; f += 32) {
+        const float v = inb ? __ldg(row + f) : 0.f;
+        bad |= !(fabsf(v) <= FLT_MAX);
+        xs[f * TB + ((sw ^ (f & 31)) | hi)] = v;
+      }
+    }
+    any_nonfinite = __syncthreads_or(bad ? 1 : 0);
+  }
+
+  const int r_begin = blockIdx.y * a.regions_per_cta;
+  const int r_end = min(a.G0, r_begin + a.regions_per_cta);
+  for (int r = r_begin + warp; r < r_end; r += 8) {
+    const int len = __ldg(a.region_len + r);
+    const int32_t* __restrict__ m = a.mask + (size_t)r * a.dim;
+    for (int c = 0; c < a.nKc; ++c) {
+      const float* __restrict__ tab = a.tab + ((size_t)r * a.nKc + c) * a.dim * ROW;
+      float acc[ST][KC];
+#pragma unroll
+      for (int s = 0; s < ST; ++s)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[s][k] = 0.f;
+
+      if (!any_nonfinite) {
+#pragma unroll 2
+        for (int d = 0; d < len; ++d) {
+          const int f = __ldg(m + d);
+          float xv[ST];
+#pragma unroll
+          for (int s = 0; s < ST; ++s) xv[s] = xs[f * TB + ((lane ^ (f & 31)) + 32 * s)];
+          float p[ROW];
+          load_row<ROW>(tab + (size_t)d * ROW, p);
+#pragma unroll
+          for (int s = 0; s < ST; ++s)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+              if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
+                const float t = fmaf(xv[s], p[k], p[KC + k]);
+                acc[s][k] = fmaf(t, t, acc[s][k]);
+              } else {
+                acc[s][k] = fmaf(xv[s], p[k], acc[s][k]);
+              }
+            }
+        }
+      } else {
+        // exact path: every term goes through nan_to_num like ratspn.py:103 (NaN = marginalised)
+        const float* __restrict__ cdt = a.cd + ((size_t)r * a.nKc + c) * a.dim * KC;
+        for (int d = 0; d < len; ++d) {
+          const int f = __ldg(m + d);
+          float xv[ST];
+#pragma unroll
+          for (int s = 0; s < ST; ++s) {
+            if constexpr (STAGE) {
+              xv[s] = xs[f * TB + ((lane ^ (f & 31)) + 32 * s)];
+            } else {
+              const int64_t b = b0 + lane + 32 * s;
+              xv[s] = (b < a.B) ? __ldg(a.x + b * a.D + f) : 0.f;
+            }
+          }
+          float p[ROW], q[KC];
+          load_row<ROW>(tab + (size_t)d * ROW, p);
+          load_row<KC>(cdt + (size_t)d * KC, q);
+#pragma unroll
+          for (int s = 0; s < ST; ++s)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+              float term;
+              if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
+                const float t = fmaf(xv[s], p[k], p[KC + k]);
+                term = fmaf(-0.5f * t, t, q[k]);
+              } else {
+                term = fmaf(xv[s], p[k], q[k]);
+              }
+              acc[s][k] += nan_to_num(term);
+            }
+        }
+      }
+
+      const float* __restrict__ cst = a.cst + (size_t)r * (KC * a.nKc) + c * KC;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int kk = c * KC + k;
+        if (kk < a.K) {
+          const float cv = __ldg(cst + k);
+#pragma unroll
+          for (int s = 0; s < ST; ++s) {
+            float v;
+            if (any_nonfinite) v = acc[s][k];
+            else if (KIND == DPK_LEAF_GAUSSIAN) v = fmaf(-0.5f, acc[s][k], cv);
+            else v = acc[s][k] + cv;
+            a.out[((size_t)r * a.K + kk) * a.Bp + b0 + lane + 32 * s] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// Product + Sum ("einsum") level and root
+// =================================================================================================
+struct EinsumArgs {
+  const float* in;     // [2P][Kin][Bp]
+  const float* wsoft;  // [P][nOc][Kin2][OC]
+  const float* wlog;
+  float* out;          // inner: [P][O][Bp]   root: (B, O) row-major
+  int64_t B, Bp;
+  int P, Kin, O, nOc, rows_per_chunk;  // rows_per_chunk: i-rows of the weight staged in smem at a time
+};
+
+constexpr int kEinsumThreads = 128;
+constexpr float kTinySum = 1e-18f;
+
+// exact log-domain value of one output (fallback): logsumexp_ij(l_i + r_j + logw[ij])
+__device__ __noinline__ float einsum_exact(const float* __restrict__ l, const float* __restrict__ r,
+                                           int64_t stride, int Kin, const float* __restrict__ wlog, int OC) {
+  float m = -INFINITY;
+  for (int i = 0; i < Kin; ++i)
+    for (int j = 0; j < Kin; ++j)
+      m = fmaxf(m, l[i * stride] + r[j * stride] + wlog[(size_t)(i * Kin + j) * OC]);
+  if (!(fabsf(m) <= FLT_MAX)) return m;  // -inf (all dropped), +inf or NaN propagate like torch.logsumexp
+  float s = 0.f;
+  for (int i = 0; i < Kin; ++i)
+    for (int j = 0; j < Kin; ++j)
+      s += expf(l[i * stride] + r[j * stride] + wlog[(size_t)(i * Kin + j) * OC] - m);
+  return m + logf(s);
+}
+
+// thread = ST samples (b = base + tid + s*128) of one partition; el/er (shifted exps) live in smem
+// [k][sample] (conflict-free), weights of the partition are staged in smem and read as broadcasts.
+template <int OC, int ST, bool ROOT>
+__global__ void __launch_bounds__(kEinsumThreads) ratspn_einsum_kernel(const EinsumArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NS = kEinsumThreads * ST;
+  float* el = sm;
+  float* er = el + (size_t)a.Kin * NS;
+  float* wsm = er + (size_t)a.Kin * NS;
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * NS;
+  const int Kin = a.Kin, Kin2 = Kin * Kin;
+
+  const int p_first = ROOT ? 0 : blockIdx.y;
+  const int p_last = ROOT ? a.P : blockIdx.y + 1;
+
+  for (int oc = 0; oc < a.nOc; ++oc) {
+    float run_m[ST], run_acc[ST][OC];  // ROOT: online logsumexp over partitions
+    if constexpr (ROOT) {
+#pragma unroll
+      for (int s = 0; s < ST; ++s) {
+        run_m[s] = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) run_acc[s][o] = 0.f;
+      }
+    }
+    for (int p = p_first; p < p_last; ++p) {
+      const float* __restrict__ lin = a.in + (size_t)(2 * p) * Kin * a.Bp;
+      const float* __restrict__ rin = lin + (size_t)Kin * a.Bp;
+      float ml[ST], mr[ST];
+      __syncthreads();  // previous users of el/er/wsm are done
+#pragma unroll
+      for (int s = 0; s < ST; ++s) {
+        const int64_t b = base + tid + s * kEinsumThreads;
+        const bool inb = b < a.Bp;
+        float vl = -INFINITY, vr = -INFINITY;
+        for (int k = 0; k < Kin; ++k) {
+          const float l = inb ? lin[(size_t)k * a.Bp + b] : 0.f;
+          const float r = inb ? rin[(size_t)k * a.Bp + b] : 0.f;
+          el[k * NS + tid + s * kEinsumThreads] = l;
+          er[k * NS + tid + s * kEinsumThreads] = r;
+          vl = fmaxf(vl, l); vr = fmaxf(vr, r);
+        }
+        // a fully -inf (dropped-out) or non-finite side: shift by 0, the exact fallback sorts it out
+        ml[s] = (fabsf(vl) <= FLT_MAX) ? vl : 0.f;
+        mr[s] = (fabsf(vr) <= FLT_MAX) ? vr : 0.f;
+        for (int k = 0; k < Kin; ++k) {
+          const int o = k * NS + tid + s * kEinsumThreads;
+          el[o] = __expf(el[o] - ml[s]);
+          er[o] = __expf(er[o] - mr[s]);
+        }
+      }
+      float acc[ST][OC];
+#pragma unroll
+      for (int s = 0; s < ST; ++s)
+#pragma unroll
+        for (int o = 0; o < OC; ++o) acc[s][o] = 0.f;
+
+      const float* __restrict__ wp = a.wsoft + ((size_t)p * a.nOc + oc) * Kin2 * OC;
+      for (int i0 = 0; i0 < Kin; i0 += a.rows_per_chunk) {
+        const int i1 = min(Kin, i0 + a.rows_per_chunk);
+        __syncthreads();
+        for (int t = tid; t < (i1 - i0) * Kin * OC; t += kEinsumThreads) wsm[t] = __ldg(wp + (size_t)i0 * Kin * OC + t);
+        __syncthreads();
+        for (int i = i0; i < i1; ++i) {
+          float eli[ST];
+#pragma unroll
+          for (int s = 0; s < ST; ++s) eli[s] = el[i * NS + tid + s * kEinsumThreads];
+          const float* wrow = wsm + (size_t)(i - i0) * Kin * OC;
+#pragma unroll 2
+          for (int j = 0; j < Kin; ++j) {
+            float w[OC];
+            load_row_smem<OC>(wrow + j * OC, w);
+#pragma unroll
+            for (int s = 0; s < ST; ++s) {
+              const float pij = eli[s] * er[j * NS + tid + s * kEinsumThreads];
+#pragma unroll
+              for (int o = 0; o < OC; ++o) acc[s][o] = fmaf(w[o], pij, acc[s][o]);
+            }
+          }
+        }
+      }
+
+      if constexpr (!ROOT) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+          const int64_t b = base + tid + s * kEinsumThreads;
+          if (b >= a.Bp) continue;
+#pragma unroll
+          for (int o = 0; o < OC; ++o) {
+            const int oo = oc * OC + o;
+            if (oo >= a.O) continue;
+            float y;
+            if (acc[s][o] >= kTinySum && acc[s][o] <= FLT_MAX)
+              y = ml[s] + mr[s] + __logf(acc[s][o]);
+            else
+              y = einsum_exact(lin + b, rin + b, a.Bp, Kin, a.wlog + ((size_t)p * a.nOc + oc) * Kin2 * OC + o, OC);
+            a.out[((size_t)p * a.O + oo) * a.Bp + b] = y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+          const float mp = ml[s] + mr[s];
+          const float nm = fmaxf(run_m[s], mp);
+          const float so = __expf(run_m[s] - nm), sn = __expf(mp - nm);  // run_m=-inf -> so = 0
+#pragma unroll
+          for (int o = 0; o < OC; ++o) run_acc[s][o] = run_acc[s][o] * so + acc[s][o] * sn;
+          run_m[s] = nm;
+        }
+      }
+    }
+    if constexpr (ROOT) {
+#pragma unroll
+      for (int s = 0; s < ST; ++s) {
+        const int64_t b = base + tid + s * kEinsumThreads;
+        if (b >= a.B) continue;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+          const int oo = oc * OC + o;
+          if (oo >= a.O) continue;
+          float y;
+          if (run_acc[s][o] >= kTinySum && run_acc[s][o] <= FLT_MAX) {
+            y = run_m[s] + __logf(run_acc[s][o]);
+          } else {
+            // exact: logsumexp over every partition
+            float m = -INFINITY, ssum = 0.f;
+            for (int p = 0; p < a.P; ++p) {
+              const float* lin = a.in + (size_t)(2 * p) * Kin * a.Bp + b;
+              const float v = einsum_exact(lin, lin + (size_t)Kin * a.Bp, a.Bp, Kin,
+                                           a.wlog + ((size_t)p * a.nOc + oc) * Kin2 * OC + o, OC);
+              if (v == -INFINITY) continue;
+              const float nm = fmaxf(m, v);
+              ssum = ssum * expf(m - nm) + expf(v - nm);
+              m = nm;
+            }
+            y = (m == -INFINITY) ? -INFINITY : m + logf(ssum);
+          }
+          a.out[(size_t)b * a.O + oo] = y;
+        }
+      }
+    }
+  }
+}
+
+// [rows][Bp] (sample-minor) -> (B, rows) row-major, for the stand-alone layer entry points
+__global__ void transpose_to_batch_major(const float* __restrict__ in, float* __restrict__ out, int rows,
+                                         int64_t B, int64_t Bp) {
+  __shared__ float tile[32][33];
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i;
+    const int64_t b = b0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && b < Bp) ? in[(size_t)r * Bp + b] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t b = b0 + i;
+    const int r = r0 + threadIdx.x;
+    if (b < B && r < rows) out[(size_t)b * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// =================================================================================================
+// Host-side launchers
+// =================================================================================================
+template <int KC, int ST, int KIND, bool STAGE>
+static int launch_leaf_t(const LeafArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = ratspn_leaf_kernel<KC, ST, KIND, STAGE>;
+  if (smem > 48 * 1024)
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(CAT_LEAF, st);
+  kern<<<grid, 256, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_leaf_kernel");
+  return DPK_OK;
+}
+
+template <int KC, int KIND>
+static int launch_leaf_k(const LeafArgs& a, int st_mode, dim3 grid, size_t smem, cudaStream_t st) {
+  switch (st_mode) {
+    case 2: return launch_leaf_t<KC, 2, KIND, true>(a, grid, smem, st);
+    case 1: return launch_leaf_t<KC, 1, KIND, true>(a, grid, smem, st);
+    default: return launch_leaf_t<KC, 1, KIND, false>(a, grid, 0, st);
+  }
+}
+
+template <int KIND>
+static int launch_leaf_kind(int KC, const LeafArgs& a, int st_mode, dim3 grid, size_t smem, cudaStream_t st) {
+  switch (KC) {
+    case 2: return launch_leaf_k<2, KIND>(a, st_mode, grid, smem, st);
+    case 4: return launch_leaf_k<4, KIND>(a, st_mode, grid, smem, st);
+    case 8: return launch_leaf_k<8, KIND>(a, st_mode, grid, smem, st);
+    case 10: return launch_leaf_k<10, KIND>(a, st_mode, grid, smem, st);
+    case 16: return launch_leaf_k<16, KIND>(a, st_mode, grid, smem, st);
+  }
+  return set_error(DPK_E_ARG, "unsupported leaf channel chunk %d", KC);
+}
+
+int ratspn_run_prep(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st) {
+  ProfScope prof(CAT_PREP, st, 3 + p.n_sum);
+  {
+    const int64_t total = (int64_t)p.G0 * p.kc.padded * p.dim;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
+    if (p.kind == DPK_LEAF_GAUSSIAN)
+      ratspn_prep_leaf_kernel<DPK_LEAF_GAUSSIAN><<<blocks, 256, 0, st>>>(
+          d->leaf_p0, d->leaf_p1, d->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
+    else
+      ratspn_prep_leaf_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(
+          d->leaf_p0, nullptr, d->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
+    DPK_LAUNCH_CHECK("ratspn_prep_leaf_kernel");
+    const int n = p.G0 * p.kc.padded;
+    ratspn_prep_const_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws + p.off_cd, d->region_len, p.G0, p.dim, p.kc.chunk,
+                                                               p.kc.count, ws + p.off_cst);
+    DPK_LAUNCH_CHECK("ratspn_prep_const_kernel");
+  }
+  for (int e = 0; e < p.n_sum; ++e) {
+    const int P = p.act_regions[e] / 2, kin2 = p.act_ch[e] * p.act_ch[e];
+    ratspn_prep_weight_kernel<<<P * p.oc.padded, 128, 0, st>>>(d->sum_weight[e], 0, P, p.O, kin2, p.oc.chunk, p.oc.count,
+                                                                ws + p.off_wsoft[e], ws + p.off_wlog[e]);
+    DPK_LAUNCH_CHECK("ratspn_prep_weight_kernel");
+  }
+  {
+    const int kin = p.act_ch[p.depth - 1];
+    ratspn_prep_weight_kernel<<<p.cc.padded, 256, 0, st>>>(d->root_weight, 1, p.R, p.C, kin * kin, p.cc.chunk, p.cc.count,
+                                                            ws + p.off_rsoft, ws + p.off_rlog);
+    DPK_LAUNCH_CHECK("ratspn_prep_weight_kernel(root)");
+  }
+  return DPK_OK;
+}
+
+int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, float* ws, cudaStream_t st) {
+  LeafArgs a;
+  a.x = x; a.mask = d->mask; a.region_len = d->region_len;
+  a.tab = ws + p.off_tab; a.cd = ws + p.off_cd; a.cst = ws + p.off_cst; a.out = ws + p.off_act[0];
+  a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
+  const size_t smem_max = (size_t)max_dynamic_smem();
+  const int nsm = sm_count();
+  // tile of 64 samples when it fits and there are enough tiles to fill the machine, else 32, else unstaged
+  int st_mode = 0;
+  if ((size_t)p.D * 64 * 4 <= smem_max && ceil_div(p.B, 64) >= nsm) st_mode = 2;
+  else if ((size_t)p.D * 32 * 4 <= smem_max) st_mode = 1;
+  const int TB = (st_mode == 2) ? 64 : 32;
+  const int64_t ntiles = ceil_div(p.B, TB);
+  // split the regions over blockIdx.y only when the batch alone cannot fill the SMs
+  int rsplit = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(2 * nsm, ntiles)), ceil_div(p.G0, 8));
+  a.regions_per_cta = (int)ceil_div(p.G0, rsplit);
+  rsplit = (int)ceil_div(p.G0, a.regions_per_cta);
+  dim3 grid((unsigned)ntiles, (unsigned)rsplit);
+  const size_t smem = st_mode ? (size_t)p.D * TB * 4 : 0;
+  if (p.kind == DPK_LEAF_GAUSSIAN) return launch_leaf_kind<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, st_mode, grid, smem, st);
+  return launch_leaf_kind<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, st_mode, grid, smem, st);
+}
+
+template <int OC, int ST, bool ROOT>
+static int launch_einsum_t(const EinsumArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = ratspn_einsum_kernel<OC, ST, ROOT>;
+  if (smem > 48 * 1024)
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(ROOT ? CAT_ROOT : CAT_EINSUM, st);
+  kern<<<grid, kEinsumThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_einsum_kernel");
+  return DPK_OK;
+}
+
+template <bool ROOT>
+static int launch_einsum(EinsumArgs a, int OC, cudaStream_t st) {
+  const size_t smem_max = (size_t)max_dynamic_smem();
+  const size_t wchunk_budget = 8192;  // bytes of weights staged at a time
+  int rows = (int)std::max<size_t>(1, wchunk_budget / ((size_t)a.Kin * OC * 4));
+  rows = std::min(rows, a.Kin);
+  a.rows_per_chunk = rows;
+  const size_t wbytes = (size_t)rows * a.Kin * OC * 4;
+  int ST = 4;
+  size_t smem = 2 * (size_t)a.Kin * kEinsumThreads * ST * 4 + wbytes;
+  if (smem > 100 * 1024 || a.Bp < 4 * kEinsumThreads) { ST = 1; smem = 2 * (size_t)a.Kin * kEinsumThreads * 4 + wbytes; }
+  if (smem > smem_max) return set_error(DPK_E_ARG, "einsum level with %d inputs per region does not fit shared memory", a.Kin);
+  dim3 grid((unsigned)ceil_div(a.Bp, kEinsumThreads * ST), ROOT ? 1u : (unsigned)a.P);
+#define DPK_EINSUM_CASE(oc)                                                             \
+  case oc:                                                                              \
+    return (ST == 4) ? launch_einsum_t<oc, 4, ROOT>(a, grid, smem, st) : launch_einsum_t<oc, 1, ROOT>(a, grid, smem, st);
+  switch (OC) {
+    DPK_EINSUM_CASE(2)
+    DPK_EINSUM_CASE(4)
+    DPK_EINSUM_CASE(8)
+    DPK_EINSUM_CASE(10)
+    DPK_EINSUM_CASE(16)
+  }
+#undef DPK_EINSUM_CASE
+  return set_error(DPK_E_ARG, "unsupported output chunk %d", OC);
+}
+
+int ratspn_run_upper(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
+  for (int e = 0; e < p.n_sum; ++e) {
+    EinsumArgs a;
+    a.in = ws + p.off_act[e]; a.wsoft = ws + p.off_wsoft[e]; a.wlog = ws + p.off_wlog[e];
+    a.out = ws + p.off_act[e + 1];
+    a.B = p.B; a.Bp = p.Bp; a.P = p.act_regions[e] / 2; a.Kin = p.act_ch[e]; a.O = p.O; a.nOc = p.oc.count;
+    int rc = launch_einsum<false>(a, p.oc.chunk, st);
+    if (rc) return rc;
+  }
+  EinsumArgs a;
+  const int l = p.depth - 1;
+  a.in = ws + p.off_act[l]; a.wsoft = ws + p.off_rsoft; a.wlog = ws + p.off_rlog; a.out = out;
+  a.B = p.B; a.Bp = p.Bp; a.P = p.R; a.Kin = p.act_ch[l]; a.O = p.C; a.nOc = p.cc.count;
+  return launch_einsum<true>(a, p.cc.chunk, st);
+}
+
+static int check_ws(const RatPlan& p, const void* ws, size_t bytes) {
+  if (!ws) return set_error(DPK_E_WORKSPACE, "null workspace");
+  if ((uintptr_t)ws % 256) return set_error(DPK_E_WORKSPACE, "workspace must be 256-byte aligned");
+  if (bytes < p.total_floats * 4)
+    return set_error(DPK_E_WORKSPACE, "workspace too small: %zu < %zu bytes", bytes, p.total_floats * 4);
+  return DPK_OK;
+}
+
+}  // namespace dpk
+
+using namespace dpk;
+
+extern "C" size_t dpk_ratspn_workspace_bytes(const dpk_ratspn_desc* desc, int64_t batch, uint32_t flags) {
+  RatPlan p;
+  if (make_plan(desc, batch, flags, &p)) return 0;
+  return p.total_floats * sizeof(float);
+}
+
+extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,
+                                  void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  RatPlan p;
+  int rc = make_plan(desc, batch, flags, &p);
+  if (rc) return rc;
+  if (batch == 0) return DPK_OK;
+  if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0 || !desc->root_weight ||
+      (p.kind == DPK_LEAF_GAUSSIAN && !desc->leaf_p1))
+    return set_error(DPK_E_ARG, "null pointer argument");
+  for (int e = 0; e < p.n_sum; ++e)
+    if (!desc->sum_weight[e]) return set_error(DPK_E_ARG, "null sum_weight[%d]", e);
+  if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+  float* ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ratspn_run_prep(desc, p, ws, st))) return rc;
+  if ((rc = ratspn_run_leaf(desc, p, x, ws, st))) return rc;
+  return ratspn_run_upper(p, ws, out, st);
+}
+
+extern "C" int dpk_ratspn_leaf_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  RatPlan p;
+  int rc = make_plan(desc, batch, 0, &p);
+  if (rc) return rc;
+  if (batch == 0) return DPK_OK;
+  if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0 || (p.kind == DPK_LEAF_GAUSSIAN && !desc->leaf_p1))
+    return set_error(DPK_E_ARG, "null pointer argument");
+  if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+  float* ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    ProfScope prof(CAT_PREP, st, 2);
+    const int64_t total = (int64_t)p.G0 * p.kc.padded * p.dim;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
+    if (p.kind == DPK_LEAF_GAUSSIAN)
+      ratspn_prep_leaf_kernel<DPK_LEAF_GAUSSIAN><<<blocks, 256, 0, st>>>(
+          desc->leaf_p0, desc->leaf_p1, desc->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
+    else
+      ratspn_prep_leaf_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(
+          desc->leaf_p0, nullptr, desc->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
+    DPK_LAUNCH_CHECK("ratspn_prep_leaf_kernel");
+    const int n = p.G0 * p.kc.padded;
+    ratspn_prep_const_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws + p.off_cd, desc->region_len, p.G0, p.dim, p.kc.chunk,
+                                                               p.kc.count, ws + p.off_cst);
+    DPK_LAUNCH_CHECK("ratspn_prep_const_kernel");
+  }
+  if ((rc = ratspn_run_leaf(desc, p, x, ws, st))) return rc;
+  const int rows = p.G0 * p.K;
+  dim3 grid((unsigned)ceil_div(p.B, 32), (unsigned)ceil_div(rows, 32));
+  ProfScope prof(CAT_LAYER, st);
+  transpose_to_batch_major<<<grid, dim3(32, 8), 0, st>>>(ws + p.off_act[0], out, rows, p.B, p.Bp);
+  DPK_LAUNCH_CHECK("transpose_to_batch_major");
+  return DPK_OK;
+}

@@ -1,0 +1,206 @@
+"""ctypes glue between the SPN nn.Modules and libdeeprob_b200.so (RAT-SPN part).
+
+Everything here is plumbing: build the POD descriptor from the module's parameters, allocate the
+workspace as a torch tensor, pass raw device pointers + the current CUDA stream to the C ABI.
+"""
+import ctypes
+from typing import List, Optional
+
+import torch
+
+from .. import _lib
+
+_PTR = ctypes.c_void_p
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous fp32 view/copy of a tensor (parameters already are: no copy in the common case)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return _PTR(t.data_ptr()) if t is not None else _PTR(0)
+
+
+class RatSpnCall:
+    """One descriptor + the tensors it borrows (kept alive for the duration of the call / autograd node)."""
+
+    def __init__(self, base_layer, sum_weights: List[torch.Tensor], root_weight: Optional[torch.Tensor],
+                 out_classes: int, sum_nodes: int, repetitions: int, device):
+        p0, p1 = base_layer.leaf_parameters()
+        self.keep = [_f32c(p0), _f32c(p1) if p1 is not None else None]
+        self.sums = [_f32c(w) for w in sum_weights]
+        self.root = _f32c(root_weight) if root_weight is not None else None
+        for t in [*self.keep, *self.sums, self.root, base_layer._mask_i32, base_layer._region_len]:
+            if t is not None and t.device != device:
+                raise RuntimeError("model parameters live on %s but the input is on %s" % (t.device, device))
+        if len(self.sums) > _lib.MAX_LEVELS:
+            raise ValueError("region graph too deep for the kernels (max %d levels)" % _lib.MAX_LEVELS)
+        d = _lib.RatSpnDesc()
+        d.leaf_kind = base_layer.leaf_kind
+        d.in_features = base_layer.in_features
+        d.depth = base_layer.rg_depth
+        d.repetitions = repetitions
+        d.leaf_channels = base_layer.out_channels
+        d.sum_nodes = sum_nodes
+        d.out_classes = out_classes
+        d.dimension = base_layer.dimension
+        d.mask = base_layer._mask_i32.data_ptr()
+        d.region_len = base_layer._region_len.data_ptr()
+        d.leaf_p0 = self.keep[0].data_ptr()
+        d.leaf_p1 = self.keep[1].data_ptr() if self.keep[1] is not None else None
+        for i, w in enumerate(self.sums):
+            d.sum_weight[i] = w.data_ptr()
+        d.root_weight = self.root.data_ptr() if self.root is not None else None
+        self.desc = d
+
+    def workspace_bytes(self, batch: int, flags: int) -> int:
+        n = _lib.lib().dpk_ratspn_workspace_bytes(ctypes.byref(self.desc), batch, flags)
+        if n == 0:
+            _lib.check(-1, "dpk_ratspn_workspace_bytes")
+        return n
+
+    def workspace(self, batch: int, flags: int, device) -> torch.Tensor:
+        return torch.empty(self.workspace_bytes(batch, flags), dtype=torch.uint8, device=device)
+
+
+def _check_input(x: torch.Tensor, features: int, what: str) -> torch.Tensor:
+    _lib.require_cuda(x, what)
+    if x.dim() != 2 or x.shape[1] != features:
+        raise ValueError("%s: expected a (batch, %d) tensor, got %s" % (what, features, tuple(x.shape)))
+    return _f32c(x)
+
+
+def ratspn_leaf_forward(layer, x: torch.Tensor) -> torch.Tensor:
+    """RegionGraphLayer.forward through dpk_ratspn_leaf_forward: (B, D) -> (B, G0, K)."""
+    x = _check_input(x, layer.in_features, "RegionGraphLayer.forward")
+    reps = layer.in_regions >> layer.rg_depth
+    call = RatSpnCall(layer, [], None, 1, 1, reps, x.device)
+    batch = x.shape[0]
+    out = torch.empty(batch, layer.in_regions, layer.out_channels, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = call.workspace(batch, 0, x.device)
+        rc = _lib.lib().dpk_ratspn_leaf_forward(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(ws),
+                                                ws.numel(), _PTR(_lib.stream_ptr(x.device)))
+    _lib.check(rc, "dpk_ratspn_leaf_forward")
+    return out
+
+
+def outer_sum_forward(x: torch.Tensor, partitions: int, nodes: int) -> torch.Tensor:
+    """ProductLayer.forward through dpk_outer_sum_forward: (B, 2P, K) -> (B, P, K*K)."""
+    _lib.require_cuda(x, "ProductLayer.forward")
+    x = _f32c(x)
+    batch = x.shape[0]
+    out = torch.empty(batch, partitions, nodes * nodes, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dpk_outer_sum_forward(_ptr(x), batch, partitions, nodes, _ptr(out),
+                                              _PTR(_lib.stream_ptr(x.device)))
+    _lib.check(rc, "dpk_outer_sum_forward")
+    return out
+
+
+def mixture_forward(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """SumLayer/RootLayer.forward through dpk_mixture_forward: (B, P, Kin) x (P, O, Kin) -> (B, P, O)."""
+    _lib.require_cuda(x, "SumLayer.forward")
+    x, w = _f32c(x), _f32c(weight.detach())
+    batch, parts, kin = x.shape
+    outs = w.shape[1]
+    out = torch.empty(batch, parts, outs, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(parts * outs, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dpk_mixture_forward(_ptr(x), _ptr(w), batch, parts, kin, outs, _ptr(out), _ptr(scratch),
+                                            _PTR(_lib.stream_ptr(x.device)))
+    _lib.check(rc, "dpk_mixture_forward")
+    return out
+
+
+class _RatSpnLogProb(torch.autograd.Function):
+    """log_prob of the whole RAT-SPN: dpk_ratspn_forward / dpk_ratspn_backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        call = model._make_call(x.device)
+        batch = x.shape[0]
+        flags = _lib.F_SAVE_ACTIVATIONS if need_grad else 0
+        out = torch.empty(batch, model.out_classes, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = model._workspace(call, batch, flags, x.device, private=need_grad)
+            rc = _lib.lib().dpk_ratspn_forward(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(ws),
+                                               ws.numel(), flags, _PTR(_lib.stream_ptr(x.device)))
+        _lib.check(rc, "dpk_ratspn_forward")
+        if need_grad:
+            ctx.call, ctx.ws, ctx.model = call, ws, model
+            ctx.save_for_backward(x, out)
+            ctx.param_shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out = ctx.saved_tensors
+        call, ws, model = ctx.call, ctx.ws, ctx.model
+        need = ctx.needs_input_grad        # (model, x, *params)
+        batch = x.shape[0]
+        g = _lib.RatSpnGrads()
+        gx = torch.zeros_like(x) if need[1] else None
+        g.grad_x = gx.data_ptr() if gx is not None else None
+        n_leaf = 2 if call.keep[1] is not None else 1
+        grads = []
+        for i, shape in enumerate(ctx.param_shapes):
+            grads.append(torch.zeros(shape, dtype=torch.float32, device=x.device) if need[2 + i] else None)
+        g.leaf_p0 = grads[0].data_ptr() if grads[0] is not None else None
+        if n_leaf == 2:
+            g.leaf_p1 = grads[1].data_ptr() if grads[1] is not None else None
+        for i in range(len(call.sums)):
+            t = grads[n_leaf + i]
+            g.sum_weight[i] = t.data_ptr() if t is not None else None
+        g.root_weight = grads[-1].data_ptr() if grads[-1] is not None else None
+        grad_out = _f32c(grad_out)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_ratspn_backward(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(grad_out),
+                                                ctypes.byref(g), _ptr(ws), ws.numel(),
+                                                _PTR(_lib.stream_ptr(x.device)))
+        _lib.check(rc, "dpk_ratspn_backward")
+        return (None, gx, *grads)
+
+
+def ratspn_log_prob(model, x: torch.Tensor) -> torch.Tensor:
+    x = _check_input(x, model.in_features, "RatSpn.forward")
+    return _RatSpnLogProb.apply(model, x, *model._kernel_parameters())
+
+
+def ratspn_em_statistics(model, x: torch.Tensor):
+    """E-step sufficient statistics of a batch (dict of tensors; see include/deeprob_b200.h)."""
+    x = _check_input(x, model.in_features, "RatSpn.em_statistics")
+    call = model._make_call(x.device)
+    batch = x.shape[0]
+    dev = x.device
+    out = torch.empty(batch, model.out_classes, dtype=torch.float32, device=dev)
+    base = model.base_layer
+    shape = (base.in_regions, base.out_channels, base.dimension)
+    stats = {
+        "sum_counts": [torch.zeros_like(w) for w in call.sums],
+        "root_counts": torch.zeros_like(call.root),
+        "s0": torch.zeros(shape, dtype=torch.float32, device=dev),
+        "s1": torch.zeros(shape, dtype=torch.float32, device=dev),
+        "s2": torch.zeros(shape, dtype=torch.float32, device=dev) if call.keep[1] is not None else None,
+    }
+    st = _lib.RatSpnEmStats()
+    for i, t in enumerate(stats["sum_counts"]):
+        st.sum_counts[i] = t.data_ptr()
+    st.root_counts = stats["root_counts"].data_ptr()
+    st.s0, st.s1 = stats["s0"].data_ptr(), stats["s1"].data_ptr()
+    st.s2 = stats["s2"].data_ptr() if stats["s2"] is not None else None
+    with torch.cuda.device(dev):
+        ws = model._workspace(call, batch, _lib.F_SAVE_ACTIVATIONS, dev, private=False)
+        sp = _PTR(_lib.stream_ptr(dev))
+        rc = _lib.lib().dpk_ratspn_forward(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(ws), ws.numel(),
+                                           _lib.F_SAVE_ACTIVATIONS, sp)
+        _lib.check(rc, "dpk_ratspn_forward")
+        rc = _lib.lib().dpk_ratspn_em_statistics(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), ctypes.byref(st),
+                                                 _ptr(ws), ws.numel(), sp)
+        _lib.check(rc, "dpk_ratspn_em_statistics")
+    stats["ll"] = out
+    return stats

@@ -1,0 +1,46 @@
+"""Host-resident batches: pipelined host->device copy, log-likelihood kernels and device->host copy.
+
+`log_prob_host` is the end-to-end entry point for data that lives in (pinned) host memory, e.g. a
+DataLoader batch as in deeprob/torch/routines.py:158-166 where the reference does
+`inputs.to(device)` -> `model(inputs)` -> `.cpu()`.  The batch is cut in chunks that alternate over
+two CUDA streams so the PCIe copies overlap the kernels.
+"""
+from typing import Optional
+
+import torch
+
+
+def log_prob_host(model, x_host: torch.Tensor, chunk: int = 16384, out_host: Optional[torch.Tensor] = None,
+                  device=None) -> torch.Tensor:
+    """x_host (B, ...) float32 CPU tensor (pinned for async copies) -> (B, C) CPU tensor of log-likelihoods."""
+    if x_host.is_cuda:
+        raise ValueError("log_prob_host expects a host tensor; call model(x) for device tensors")
+    dev = torch.device(device) if device is not None else next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("the model must live on a CUDA device (no CPU path)")
+    n = x_host.shape[0]
+    cache = model.__dict__.setdefault("_host_pipeline", {})
+    key = (str(dev), chunk, tuple(x_host.shape[1:]))
+    if key not in cache:
+        cache[key] = {
+            "streams": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)],
+            "bufs": [torch.empty((chunk, *x_host.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)],
+        }
+    streams, bufs = cache[key]["streams"], cache[key]["bufs"]
+    cur = torch.cuda.current_stream(dev)
+    for s in streams:
+        s.wait_stream(cur)
+    with torch.no_grad():
+        for i, start in enumerate(range(0, n, chunk)):
+            m = min(chunk, n - start)
+            s = streams[i % 2]
+            with torch.cuda.stream(s):
+                xb = bufs[i % 2][:m]
+                xb.copy_(x_host[start:start + m], non_blocking=True)
+                y = model(xb)
+                if out_host is None:
+                    out_host = torch.empty((n, *y.shape[1:]), dtype=torch.float32, pin_memory=True)
+                out_host[start:start + m].copy_(y, non_blocking=True)
+    for s in streams:
+        cur.wait_stream(s)
+    return out_host

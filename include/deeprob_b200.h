@@ -1,0 +1,137 @@
+/* deeprob_b200.h -- C ABI of libdeeprob_b200.so (hand-written sm_100a kernels for the deeprob-kit
+ * tensorised log-likelihood path).
+ *
+ * The reference (deeprob-kit @ d96ac30) is pure Python on stock PyTorch ops: there is no FFI to
+ * re-bind, so every entry point below cites the reference *Python* interface it replaces.  The
+ * Python host side (package deeprob_kit_b200) binds these with ctypes; INTEGRATION.md shows the
+ * stub a deeprob-kit maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host"; buffers are borrowed for the
+ *     duration of the stream-ordered launches only (the caller -- PyTorch -- owns all memory);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value 0 = success, negative = error (DPK_E_*); text via dpk_last_error() (thread-local);
+ *   - no global mutable state besides a per-process cache of device attributes; re-entrant per stream.
+ */
+#ifndef DEEPROB_B200_H_
+#define DEEPROB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPK_ABI_VERSION 1
+#define DPK_MAX_LEVELS 16
+
+#define DPK_OK 0
+#define DPK_E_ARG (-1)      /* bad shape / null pointer / unsupported size */
+#define DPK_E_WORKSPACE (-2) /* workspace too small or misaligned */
+#define DPK_E_CUDA (-3)     /* a CUDA runtime call failed (message has the CUDA error string) */
+
+#define DPK_LEAF_GAUSSIAN 0
+#define DPK_LEAF_BERNOULLI 1
+
+/* flags */
+#define DPK_F_SAVE_ACTIVATIONS 1 /* forward keeps per-level activations in the workspace for backward */
+
+int dpk_abi_version(void);
+const char* dpk_last_error(void);
+
+/* Launch accounting for benchmarks/tests (no reference counterpart): every kernel launch of the
+ * library is counted per category; with profiling enabled each launch group is also bracketed by
+ * CUDA events on its stream.  dpk_profile_read fills `ms` (elapsed, only while enabled) and
+ * `launches` (always) for categories 0..ncat-1 since the previous read, and resets them.
+ * Categories: 0 prep, 1 ratspn leaf, 2 ratspn product+sum, 3 ratspn root, 4 ratspn bwd product+sum,
+ * 5 ratspn bwd leaf, 6 finalize, 7 stand-alone layers, 8 dgcspn fwd, 9 dgcspn bwd, 10 flow fwd,
+ * 11 flow bwd, 12 gemm. */
+#define DPK_PROFILE_CATEGORIES 16
+int dpk_profile_enable(int on);
+int dpk_profile_read(double* ms, int64_t* launches, int32_t ncat);
+
+/* ------------------------------------------------------------------------------------------------
+ * RAT-SPN  (deeprob/spn/models/ratspn.py:105-122 RatSpn.forward and the layers it chains:
+ *   RegionGraphLayer.forward  deeprob/spn/layers/ratspn.py:87-108   (Gaussian :160-213, Bernoulli :216-247)
+ *   ProductLayer.forward      deeprob/spn/layers/ratspn.py:272-286
+ *   SumLayer.forward          deeprob/spn/layers/ratspn.py:363-378
+ *   RootLayer.forward         deeprob/spn/layers/ratspn.py:446-458 )
+ * Structure: G0 = repetitions * 2^depth leaf regions of `dimension` gathered features and
+ * `leaf_channels` densities each; depth products, depth-1 inner sum levels, one root.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dpk_ratspn_desc {
+  int32_t leaf_kind;     /* DPK_LEAF_* */
+  int32_t in_features;   /* D */
+  int32_t depth;         /* rg_depth >= 1 */
+  int32_t repetitions;   /* rg_repetitions */
+  int32_t leaf_channels; /* K = rg_batch */
+  int32_t sum_nodes;     /* O = rg_sum */
+  int32_t out_classes;   /* C */
+  int32_t dimension;     /* ceil(D / 2^depth) */
+  const int32_t* mask;       /* (G0, dimension) int32 copy of base_layer.mask (ratspn.py:47-56) */
+  const int32_t* region_len; /* (G0) number of real (non-pad) features of each region */
+  const float* leaf_p0;      /* (G0, K, dimension) loc | logits */
+  const float* leaf_p1;      /* (G0, K, dimension) scale, NULL for Bernoulli */
+  const float* sum_weight[DPK_MAX_LEVELS]; /* host array: level l raw logits (G0>>(l+1), O, Kin_l) */
+  const float* root_weight;  /* (C, repetitions * Kin_last) raw logits */
+} dpk_ratspn_desc;
+
+/* gradient / statistic outputs of dpk_ratspn_backward; any pointer may be NULL = not wanted.
+ * All are ACCUMULATED INTO (caller zero-fills), fp32, same shapes as the parameters. */
+typedef struct dpk_ratspn_grads {
+  float* grad_x;        /* (B, D) */
+  float* leaf_p0;       /* d/dloc or d/dlogits */
+  float* leaf_p1;       /* d/dscale */
+  float* sum_weight[DPK_MAX_LEVELS];
+  float* root_weight;
+} dpk_ratspn_grads;
+
+/* EM sufficient statistics (extension; semantics of deeprob/spn/learning/em.py:99-107 on the
+ * tensorised model): posterior counts of every sum/root weight and leaf moments. */
+typedef struct dpk_ratspn_em_stats {
+  float* sum_counts[DPK_MAX_LEVELS]; /* like sum_weight */
+  float* root_counts;                /* like root_weight */
+  float* s0;                         /* (G0, K, dimension) sum_b post * [x observed] */
+  float* s1;                         /* (G0, K, dimension) sum_b post * x */
+  float* s2;                         /* (G0, K, dimension) sum_b post * x^2 (Gaussian only, may be NULL) */
+} dpk_ratspn_em_stats;
+
+/* bytes of scratch the forward (and, with DPK_F_SAVE_ACTIVATIONS, the following backward) needs */
+size_t dpk_ratspn_workspace_bytes(const dpk_ratspn_desc* desc, int64_t batch, uint32_t flags);
+
+/* x (B, D) fp32 row-major, NaN = marginalised variable; out (B, C) fp32 */
+int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,
+                       void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* backward of sum_{b,c} grad_out[b,c] * out[b,c]; `workspace` is the one the forward filled with
+ * DPK_F_SAVE_ACTIVATIONS; `out` the forward result. */
+int dpk_ratspn_backward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, const float* out,
+                        const float* grad_out, const dpk_ratspn_grads* grads, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* E-step statistics of the batch (grad_out == 1 for the class column `cls`, posterior form). */
+int dpk_ratspn_em_statistics(const dpk_ratspn_desc* desc, const float* x, int64_t batch,
+                             const float* out, const dpk_ratspn_em_stats* stats, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Stand-alone layers with the reference layouts (used by the nn.Module layer classes). */
+/* RegionGraphLayer.forward: out (B, G0, K) */
+int dpk_ratspn_leaf_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ProductLayer.forward (deeprob/spn/layers/ratspn.py:272-286): x (B, 2P, K) -> out (B, P, K*K),
+ * out[b,p,i*K+j] = x[b,2p,i] + x[b,2p+1,j] */
+int dpk_outer_sum_forward(const float* x, int64_t batch, int32_t partitions, int32_t nodes, float* out,
+                          void* stream);
+
+/* SumLayer.forward (ratspn.py:363-378) / RootLayer.forward (:446-458, partitions = 1):
+ * x (B, P, Kin), weight (P, O, Kin) raw logits -> out (B, P, O) = logsumexp_k(x + log_softmax_k(weight));
+ * scratch: P*O floats. Exact log-domain evaluation. */
+int dpk_mixture_forward(const float* x, const float* weight, int64_t batch, int32_t partitions,
+                        int32_t in_nodes, int32_t out_nodes, float* out, float* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPROB_B200_H_ */

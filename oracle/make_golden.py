@@ -1,0 +1,77 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference).
+
+Run here (the CPU container):   python oracle/make_golden.py [ratspn|dgcspn|flows|all]
+The fixtures hold only reference outputs (+ tiny index tables); parameters and inputs are
+re-created from tests/param_gen.py by seed.  Test infrastructure only.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_env  # noqa: E402
+
+ref_env.enable()
+import param_gen as pg  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def make_ratspn():
+    from deeprob.spn.models.ratspn import GaussianRatSpn, BernoulliRatSpn
+    from deeprob.utils.region import RegionGraph
+
+    # region-graph structure goldens (tests/test_ratspn.py:24-43 uses (15, 2, seed 42, 2 reps))
+    rg = {}
+    for (d, depth, reps, seed) in [(15, 2, 2, 42), (16, 2, 1, 42), (784, 3, 4, 42), (37, 3, 5, 7), (64, 5, 2, 0)]:
+        layers = RegionGraph(d, depth, seed).make_layers(reps)
+        leaf = layers[-1]
+        width = max(len(r) for r in leaf)
+        tab = -np.ones((len(leaf), width), np.int64)
+        for i, r in enumerate(leaf):
+            tab[i, :len(r)] = r
+        rg["leaf_%d_%d_%d_%d" % (d, depth, reps, seed)] = tab
+    np.savez_compressed(os.path.join(GOLDEN, "region_graph.npz"), **rg)
+
+    for name, cfg in pg.RATSPN_CASES.items():
+        cls = GaussianRatSpn if cfg["kind"] == "gaussian" else BernoulliRatSpn
+        torch.manual_seed(0)
+        model = cls(**pg.ratspn_ctor_kwargs(cfg)).eval()
+        model.load_state_dict(pg.ratspn_fill_state(model.state_dict(), cfg))
+        if cfg["kind"] == "gaussian":
+            model.base_layer.scale.requires_grad_(True)     # golden d/dscale even when the ctor froze it
+        x, g = pg.ratspn_inputs(cfg)
+        xg = x.clone().requires_grad_(True)
+        out = model(xg)
+        (out * g).sum().backward()
+        rec = {"ll": _np(out), "mask": _np(model.base_layer.mask).astype(np.int32)}
+        small = cfg["in_features"] <= 64
+        grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        for k, v in grads.items():
+            v = _np(v)
+            rec["grad." + k] = v if (small or v.size <= 20000) else v.reshape(-1)[:: max(1, v.size // 4096)]
+        gx = _np(torch.nan_to_num(xg.grad))
+        rec["grad.x"] = gx if small else gx[:8]
+        np.savez_compressed(os.path.join(GOLDEN, "ratspn_%s.npz" % name), **rec)
+        print("ratspn", name, "ll[:3]=", rec["ll"].reshape(-1)[:3])
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    os.makedirs(GOLDEN, exist_ok=True)
+    if what in ("ratspn", "all"):
+        make_ratspn()
+    if what in ("dgcspn", "all") and "make_dgcspn" in globals():
+        globals()["make_dgcspn"]()
+    if what in ("flows", "all") and "make_flows" in globals():
+        globals()["make_flows"]()

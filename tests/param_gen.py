@@ -1,0 +1,85 @@
+"""Deterministic (numpy-seeded) parameters and inputs shared by the golden generator and the tests.
+
+Keeping parameters a pure function of (config, seed) lets the golden fixtures store only the
+reference OUTPUTS; the same state is loaded into the reference (oracle/make_golden.py), into the
+CPU oracle and into the CUDA-backed modules through the reference's `state_dict` keys.
+"""
+import numpy as np
+import torch
+
+# name -> constructor config of a RAT-SPN case (keys follow deeprob/spn/models/ratspn.py:17-30,195-208)
+RATSPN_CASES = {
+    # BASELINE config 1 as written: Bernoulli D=16 depth 2 K=2 batch 128
+    "bern16": dict(kind="bernoulli", in_features=16, rg_depth=2, rg_repetitions=1, rg_batch=2, rg_sum=2,
+                   out_classes=1, batch=128, nan_frac=0.0, binary=True),
+    # the shape tests/test_ratspn.py:18-21 really uses (pad>0: 15 % 8 != 0)
+    "bern15": dict(kind="bernoulli", in_features=15, rg_depth=3, rg_repetitions=4, rg_batch=4, rg_sum=2,
+                   out_classes=1, batch=256, nan_frac=0.0, binary=True),
+    "bern15_nan": dict(kind="bernoulli", in_features=15, rg_depth=3, rg_repetitions=4, rg_batch=4, rg_sum=2,
+                       out_classes=1, batch=256, nan_frac=0.5, binary=True),
+    # depth 1: no inner sum layer at all (Product -> Root)
+    "gauss_d1": dict(kind="gaussian", in_features=9, rg_depth=1, rg_repetitions=3, rg_batch=5, rg_sum=3,
+                     out_classes=1, batch=64, nan_frac=0.0, optimize_scale=True),
+    # classes > 1, odd sizes, padding, learnable scale, NaNs
+    "gauss_cls": dict(kind="gaussian", in_features=37, rg_depth=3, rg_repetitions=5, rg_batch=6, rg_sum=7,
+                      out_classes=4, batch=96, nan_frac=0.2, optimize_scale=True),
+    "gauss_deep": dict(kind="gaussian", in_features=64, rg_depth=5, rg_repetitions=2, rg_batch=3, rg_sum=4,
+                       out_classes=2, batch=80, nan_frac=0.0, optimize_scale=False),
+    # north-star structure (BASELINE config 2) on a small batch
+    "gauss784": dict(kind="gaussian", in_features=784, rg_depth=3, rg_repetitions=16, rg_batch=10, rg_sum=10,
+                     out_classes=1, batch=192, nan_frac=0.0, optimize_scale=False),
+    "gauss784_scale_nan": dict(kind="gaussian", in_features=784, rg_depth=3, rg_repetitions=16, rg_batch=10,
+                               rg_sum=10, out_classes=1, batch=64, nan_frac=0.1, optimize_scale=True),
+    "bern784": dict(kind="bernoulli", in_features=784, rg_depth=4, rg_repetitions=8, rg_batch=16, rg_sum=12,
+                    out_classes=10, batch=64, nan_frac=0.0, binary=True),
+}
+RATSPN_SEED = 42          # region-graph random_state used by every case
+
+
+def ratspn_ctor_kwargs(cfg):
+    kw = {k: cfg[k] for k in ("in_features", "rg_depth", "rg_repetitions", "rg_batch", "rg_sum", "out_classes")}
+    kw["random_state"] = RATSPN_SEED
+    if cfg["kind"] == "gaussian":
+        kw["optimize_scale"] = cfg.get("optimize_scale", False)
+    return kw
+
+
+def _log_dirichlet(rng, shape):
+    g = rng.gamma(1.0, 1.0, size=shape).astype(np.float64) + 1e-12
+    return np.log(g / g.sum(-1, keepdims=True)).astype(np.float32)
+
+
+def ratspn_fill_state(state, cfg, seed=0):
+    """Overwrite every learnable tensor of a reference-keyed state_dict in place (sorted-key order)."""
+    rng = np.random.RandomState(1000 + seed)
+    out = {}
+    for key in sorted(state.keys()):
+        t = state[key]
+        if key == "base_layer.loc" or key == "base_layer.logits":
+            v = rng.standard_normal(t.shape).astype(np.float32)
+        elif key == "base_layer.scale":
+            if cfg.get("optimize_scale", False):
+                v = (0.35 + 0.9 * rng.random_sample(t.shape)).astype(np.float32)
+            else:
+                v = np.ones(t.shape, np.float32)
+        elif key.endswith(".weight"):
+            v = _log_dirichlet(rng, tuple(t.shape)) + rng.standard_normal((*t.shape[:-1], 1)).astype(np.float32)
+        else:
+            out[key] = t
+            continue
+        out[key] = torch.from_numpy(v)
+    return out
+
+
+def ratspn_inputs(cfg, seed=0):
+    rng = np.random.RandomState(2000 + seed)
+    b, d = cfg["batch"], cfg["in_features"]
+    if cfg.get("binary", False):
+        x = (rng.random_sample((b, d)) < 0.5).astype(np.float32)
+    else:
+        x = rng.standard_normal((b, d)).astype(np.float32)
+    if cfg.get("nan_frac", 0.0) > 0:
+        x[rng.random_sample((b, d)) < cfg["nan_frac"]] = np.nan
+        x[0, :] = np.nan              # one fully marginalised row: LL must be ~0
+    g = rng.standard_normal((b, cfg["out_classes"])).astype(np.float32)
+    return torch.from_numpy(x), torch.from_numpy(g)

