@@ -371,7 +371,7 @@ struct LeafBwdXArgs {
   const float* x;
   const int32_t* mask;
   const int32_t* region_len;
-  const float* tab;  // forward table [G0][nKc][dim][NP*KC]
+  const float* tab;  // forward table [G0][nKc][dim][ROWP]
   const float* g0;   // [G0][K][Bp]
   float* gx;         // (B, D), accumulated
   int64_t B, Bp;
@@ -382,7 +382,8 @@ template <int KC, int KIND, bool STAGE>
 __global__ void __launch_bounds__(256) ratspn_leaf_bwd_x_kernel(const LeafBwdXArgs a) {
   extern __shared__ __align__(16) float sm[];
   constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;
-  constexpr int ROW = NP * KC;
+  constexpr int NPK = (NP * KC + 3) / 4 * 4;
+  constexpr int ROW = 4 + NPK;          // table row: {feature index, pad x3, values}
   float* xs = sm;                       // [D][32] swizzled
   float* gxs = sm + (size_t)a.D * 32;   // [D][32] swizzled
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -416,8 +417,8 @@ __global__ void __launch_bounds__(256) ratspn_leaf_bwd_x_kernel(const LeafBwdXAr
         float xv;
         if constexpr (STAGE) xv = xs[ff * 32 + (lane ^ (ff & 31))];
         else xv = (b < a.B) ? __ldg(a.x + b * a.D + ff) : 0.f;
-        float p[ROW];
-        load_row<ROW>(tab + (size_t)d * ROW, p);
+        float p[NPK];
+        load_row<NPK>(tab + (size_t)d * ROW + 4, p);
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {

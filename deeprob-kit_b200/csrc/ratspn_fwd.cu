@@ -23,8 +23,9 @@ namespace dpk {
 // =================================================================================================
 template <int KIND>
 __global__ void ratspn_prep_leaf_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
-                                        const int32_t* __restrict__ region_len, int G0, int K, int dim,
-                                        int KC, int nKc, float* __restrict__ tab, float* __restrict__ cd) {
+                                        const int32_t* __restrict__ mask, const int32_t* __restrict__ region_len,
+                                        int G0, int K, int dim, int KC, int nKc, int rowp,
+                                        float* __restrict__ tab, float* __restrict__ cd) {
   const int Kp = KC * nKc;
   const int64_t total = (int64_t)G0 * Kp * dim;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -33,9 +34,16 @@ __global__ void ratspn_prep_leaf_kernel(const float* __restrict__ p0, const floa
     const int kk = (int)((idx / dim) % Kp);
     const int g = (int)(idx / ((int64_t)dim * Kp));
     const int c = kk / KC, k = kk % KC;
-    const bool live = kk < K && d < region_len[g];
+    const bool live = kk < K && d < region_len[g];   // pad dims / pad channels contribute exactly 0
     const size_t src = ((size_t)g * K + kk) * dim + d;
     const size_t row = ((size_t)g * nKc + c) * dim + d;
+    float* trow = tab + row * rowp;
+    if (k == 0) {
+      trow[0] = __int_as_float(mask[(size_t)g * dim + d]);
+      trow[1] = 0.f; trow[2] = 0.f; trow[3] = 0.f;
+      const int used = 4 + ((KIND == DPK_LEAF_GAUSSIAN) ? 2 * KC : KC);
+      for (int z = used; z < rowp; ++z) trow[z] = 0.f;
+    }
     if (KIND == DPK_LEAF_GAUSSIAN) {
       float rs = 0.f, mr = 0.f, cdv = 0.f;
       if (live) {
@@ -44,8 +52,8 @@ __global__ void ratspn_prep_leaf_kernel(const float* __restrict__ p0, const floa
         mr = -mu * rs;
         cdv = -logf(sigma) - kLogSqrt2Pi;
       }
-      tab[row * 2 * KC + k] = rs;
-      tab[row * 2 * KC + KC + k] = mr;
+      trow[4 + k] = rs;
+      trow[4 + KC + k] = mr;
       cd[row * KC + k] = cdv;
     } else {
       float lg = 0.f, cdv = 0.f;
@@ -53,7 +61,7 @@ __global__ void ratspn_prep_leaf_kernel(const float* __restrict__ p0, const floa
         lg = p0[src];
         cdv = -(fmaxf(lg, 0.f) + log1pf(expf(-fabsf(lg))));  // -softplus(logit)
       }
-      tab[row * KC + k] = lg;
+      trow[4 + k] = lg;
       cd[row * KC + k] = cdv;
     }
   }
@@ -128,131 +136,260 @@ __global__ void ratspn_prep_weight_kernel(const float* __restrict__ src, int mod
 // =================================================================================================
 struct LeafArgs {
   const float* x;            // (B, D)
-  const int32_t* mask;       // (G0, dim)
   const int32_t* region_len; // (G0)
-  const float* tab;          // [G0][nKc][dim][NP*KC]
+  const float* tab;          // [G0][nKc][dim][ROWP]
   const float* cd;           // [G0][nKc][dim][KC]
   const float* cst;          // [G0][Kp]
   float* out;                // [G0][K][Bp]
   int64_t B, Bp;
   int D, G0, K, dim, nKc, regions_per_cta;
+  int ring_rows;             // CH: table rows per ring stage
 };
 
-// One CTA = one tile of TB = 32*ST samples x a contiguous range of regions.  8 warps; a warp owns a
-// region at a time, lanes = samples, so the per-(region,dim) parameters are warp-uniform broadcast
-// loads and the x reads from the transposed tile are bank-conflict free.
-// Shared tile layout: element (feature f, sample s) at f*TB + ((s&31) ^ (f&31)) + (s & ~31):
-// conflict-free both for the transposing fill (lanes = features) and for the sweep (lanes = samples).
-template <int KC, int ST, int KIND, bool STAGE>
-__global__ void __launch_bounds__(256) ratspn_leaf_kernel(const LeafArgs a) {
-  extern __shared__ __align__(16) float xs[];
+constexpr int kLeafStages = 4;  // per-warp ring depth of TMA-bulk parameter chunks
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// One CTA = one tile of TB = 32*ST samples x a contiguous range of regions, 8 warps.
+//  * the x tile is staged ONCE, transposed, with asynchronous 4-byte copies:
+//      element (feature f, sample s) at f*TB + ((s&31) ^ (f&31)) + (s & ~31)
+//    (conflict-free for the fill, lanes = features, and for the sweep, lanes = samples);
+//  * a warp owns one region at a time, lanes = samples, accumulators for ST samples x KC channels
+//    live in registers; the (feature index, 1/sigma, -mu/sigma) rows of the region stream through a
+//    warp-private ring of TMA bulk copies (cp.async.bulk + mbarrier), so the inner loop only issues
+//    warp-uniform (broadcast) shared loads;
+//  * 2 packed FFMA2 per pair of channels and feature:  t = x*rs + mr ; acc += t*t.
+// A non-finite input makes the fast result non-finite; that is detected per region and the region is
+// redone on the exact path, which applies nan_to_num term by term like ratspn.py:103.
+template <int KC, int ST, int KIND>
+__global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int TB = 32 * ST;
   constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;
-  constexpr int ROW = NP * KC;
+  constexpr int NPK = (NP * KC + 3) / 4 * 4;
+  constexpr int ROWP = 4 + NPK;
+  constexpr int KH = KC / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * TB;
+  const int CH = a.ring_rows;
 
-  int any_nonfinite = 1;  // unstaged variant: always take the exact nan_to_num path
-  if constexpr (STAGE) {
-    bool bad = false;
-    for (int s = warp; s < TB; s += 8) {
-      const int64_t b = b0 + s;
-      const bool inb = b < a.B;
-      const float* row = a.x + b * a.D;
-      const int sw = s & 31, hi = s & ~31;
-#pragma unroll 4
-      for (int f = lane; f < a.D; f += 32) {
-        const float v = inb ? __ldg(row + f) : 0.f;
-        bad |= !(fabsf(v) <= FLT_MAX);
-        xs[f * TB + ((sw ^ (f & 31)) | hi)] = v;
-      }
-    }
-    any_nonfinite = __syncthreads_or(bad ? 1 : 0);
-  }
+  float* xs = reinterpret_cast<float*>(smem_raw);
+  float* ring = xs + (size_t)a.D * TB + (size_t)warp * kLeafStages * CH * ROWP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xs + (size_t)a.D * TB + (size_t)8 * kLeafStages * CH * ROWP) +
+                   warp * kLeafStages;
 
+  // ---- this warp's work list: regions r_begin+warp, +8, ... ; nKc channel chunks each ----------
   const int r_begin = blockIdx.y * a.regions_per_cta;
   const int r_end = min(a.G0, r_begin + a.regions_per_cta);
-  for (int r = r_begin + warp; r < r_end; r += 8) {
-    const int len = __ldg(a.region_len + r);
-    const int32_t* __restrict__ m = a.mask + (size_t)r * a.dim;
+  const int n_reg = (r_end - r_begin - warp + 7) / 8;          // may be <= 0
+  const int NCH = (a.dim + CH - 1) / CH;
+  const int n_chunks = max(n_reg, 0) * a.nKc * NCH;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kLeafStages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  // producer cursor (lane 0 issues): chunk q -> (region, channel chunk, row chunk)
+  int pq = 0, p_reg = r_begin + warp, p_c = 0, p_ch = 0;
+  auto issue = [&]() {
+    if (pq < n_chunks) {
+      if (lane == 0) {
+        const int rows = min(CH, a.dim - p_ch * CH);
+        const float* src = a.tab + (((size_t)p_reg * a.nKc + p_c) * a.dim + (size_t)p_ch * CH) * ROWP;
+        const int stage = pq % kLeafStages;
+        const uint32_t bytes = (uint32_t)rows * ROWP * 4;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bars + stage, bytes);
+        bulk_g2s(ring + (size_t)stage * CH * ROWP, src, bytes, bars + stage);
+      }
+      ++pq;
+      if (++p_ch == NCH) { p_ch = 0; if (++p_c == a.nKc) { p_c = 0; p_reg += 8; } }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < kLeafStages - 1; ++s) issue();
+
+  // ---- x tile: asynchronous transposing fill -------------------------------------------------
+  for (int s = warp; s < TB; s += 8) {
+    const int64_t b = b0 + s;
+    const bool inb = b < a.B;
+    const float* row = a.x + (inb ? b : 0) * a.D;
+    const int sw = s & 31, hi = s & ~31;
+    for (int f = lane; f < a.D; f += 32) cp_async_4(xs + f * TB + ((sw ^ (f & 31)) | hi), row + f, inb ? 4u : 0u);
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- sweep ------------------------------------------------------------------------------------
+  int q = 0;
+  for (int ri = 0; ri < n_reg; ++ri) {
+    const int r = r_begin + warp + 8 * ri;
     for (int c = 0; c < a.nKc; ++c) {
-      const float* __restrict__ tab = a.tab + ((size_t)r * a.nKc + c) * a.dim * ROW;
-      float acc[ST][KC];
+      float2 acc[ST][KH];
 #pragma unroll
       for (int s = 0; s < ST; ++s)
 #pragma unroll
-        for (int k = 0; k < KC; ++k) acc[s][k] = 0.f;
+        for (int k = 0; k < KH; ++k) acc[s][k] = make_float2(0.f, 0.f);
 
-      if (!any_nonfinite) {
+      for (int ch = 0; ch < NCH; ++ch, ++q) {
+        issue();                                         // keep kLeafStages-1 chunks in flight
+        const int stage = q % kLeafStages;
+        mbar_wait(bars + stage, (q / kLeafStages) & 1);
+        const float* __restrict__ rows = ring + (size_t)stage * CH * ROWP;
+        const int nrows = min(CH, a.dim - ch * CH);
 #pragma unroll 2
-        for (int d = 0; d < len; ++d) {
-          const int f = __ldg(m + d);
-          float xv[ST];
-#pragma unroll
-          for (int s = 0; s < ST; ++s) xv[s] = xs[f * TB + ((lane ^ (f & 31)) + 32 * s)];
-          float p[ROW];
-          load_row<ROW>(tab + (size_t)d * ROW, p);
-#pragma unroll
-          for (int s = 0; s < ST; ++s)
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-              if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
-                const float t = fmaf(xv[s], p[k], p[KC + k]);
-                acc[s][k] = fmaf(t, t, acc[s][k]);
-              } else {
-                acc[s][k] = fmaf(xv[s], p[k], acc[s][k]);
-              }
-            }
-        }
-      } else {
-        // exact path: every term goes through nan_to_num like ratspn.py:103 (NaN = marginalised)
-        const float* __restrict__ cdt = a.cd + ((size_t)r * a.nKc + c) * a.dim * KC;
-        for (int d = 0; d < len; ++d) {
-          const int f = __ldg(m + d);
-          float xv[ST];
+        for (int d = 0; d < nrows; ++d) {
+          const float4 head = *reinterpret_cast<const float4*>(rows + d * ROWP);
+          const int f = __float_as_int(head.x);
+          float p[NPK];
+          load_row_smem<NPK>(rows + d * ROWP + 4, p);
+          const int at = f * TB + (lane ^ (f & 31));
 #pragma unroll
           for (int s = 0; s < ST; ++s) {
-            if constexpr (STAGE) {
-              xv[s] = xs[f * TB + ((lane ^ (f & 31)) + 32 * s)];
-            } else {
-              const int64_t b = b0 + lane + 32 * s;
-              xv[s] = (b < a.B) ? __ldg(a.x + b * a.D + f) : 0.f;
+            const float xv = xs[at + 32 * s];
+            const float2 x2 = make_float2(xv, xv);
+#pragma unroll
+            for (int k = 0; k < KH; ++k) {
+              if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
+                const float2 t = __ffma2_rn(x2, make_float2(p[2 * k], p[2 * k + 1]),
+                                            make_float2(p[KC + 2 * k], p[KC + 2 * k + 1]));
+                acc[s][k] = __ffma2_rn(t, t, acc[s][k]);
+              } else {
+                acc[s][k] = __ffma2_rn(x2, make_float2(p[2 * k], p[2 * k + 1]), acc[s][k]);
+              }
             }
           }
-          float p[ROW], q[KC];
-          load_row<ROW>(tab + (size_t)d * ROW, p);
-          load_row<KC>(cdt + (size_t)d * KC, q);
+        }
+        __syncwarp();                                    // every lane is done with this stage
+      }
+
+      // ---- finish the (region, channel chunk): constants, non-finite check, store -------------
+      const float* __restrict__ cst = a.cst + (size_t)r * (KC * a.nKc) + c * KC;
+      float val[ST][KC];
+      bool bad = false;
 #pragma unroll
-          for (int s = 0; s < ST; ++s)
+      for (int k = 0; k < KC; ++k) {
+        const float cv = __ldg(cst + k);
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+          const float av = (k & 1) ? acc[s][k / 2].y : acc[s][k / 2].x;
+          val[s][k] = (KIND == DPK_LEAF_GAUSSIAN) ? fmaf(-0.5f, av, cv) : av + cv;
+          bad |= !(fabsf(val[s][k]) <= FLT_MAX);
+        }
+      }
+      if (__any_sync(0xffffffffu, bad)) {
+        // exact path for this region: every term goes through nan_to_num like ratspn.py:103
+        const float* __restrict__ tab = a.tab + ((size_t)r * a.nKc + c) * a.dim * ROWP;
+        const float* __restrict__ cdt = a.cd + ((size_t)r * a.nKc + c) * a.dim * KC;
+        const int len = __ldg(a.region_len + r);
+#pragma unroll
+        for (int s = 0; s < ST; ++s)
+#pragma unroll
+          for (int k = 0; k < KC; ++k) val[s][k] = 0.f;
+        for (int d = 0; d < len; ++d) {
+          const int f = __float_as_int(__ldg(tab + (size_t)d * ROWP));
+          float p[NPK], qd[KC];
+          load_row<NPK>(tab + (size_t)d * ROWP + 4, p);
+          load_row<KC>(cdt + (size_t)d * KC, qd);
+#pragma unroll
+          for (int s = 0; s < ST; ++s) {
+            const float xv = xs[f * TB + (lane ^ (f & 31)) + 32 * s];
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
               float term;
               if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
-                const float t = fmaf(xv[s], p[k], p[KC + k]);
-                term = fmaf(-0.5f * t, t, q[k]);
+                const float t = fmaf(xv, p[k], p[KC + k]);
+                term = fmaf(-0.5f * t, t, qd[k]);
               } else {
-                term = fmaf(xv[s], p[k], q[k]);
+                term = fmaf(xv, p[k], qd[k]);
               }
-              acc[s][k] += nan_to_num(term);
+              val[s][k] += nan_to_num(term);
             }
+          }
         }
       }
-
-      const float* __restrict__ cst = a.cst + (size_t)r * (KC * a.nKc) + c * KC;
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
         const int kk = c * KC + k;
         if (kk < a.K) {
-          const float cv = __ldg(cst + k);
 #pragma unroll
-          for (int s = 0; s < ST; ++s) {
-            float v;
-            if (any_nonfinite) v = acc[s][k];
-            else if (KIND == DPK_LEAF_GAUSSIAN) v = fmaf(-0.5f, acc[s][k], cv);
-            else v = acc[s][k] + cv;
-            a.out[((size_t)r * a.K + kk) * a.Bp + b0 + lane + 32 * s] = v;
-          }
+          for (int s = 0; s < ST; ++s) a.out[((size_t)r * a.K + kk) * a.Bp + b0 + lane + 32 * s] = val[s][k];
         }
+      }
+    }
+  }
+}
+
+// Fallback for inputs too wide for a shared-memory tile: x is gathered straight from global/L2 and
+// every term takes the exact path.  Correct for any D, not tuned.
+template <int KC, int KIND>
+__global__ void __launch_bounds__(256) ratspn_leaf_wide_kernel(const LeafArgs a) {
+  constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;
+  constexpr int NPK = (NP * KC + 3) / 4 * 4;
+  constexpr int ROWP = 4 + NPK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * 32 + lane;
+  const int r_begin = blockIdx.y * a.regions_per_cta;
+  const int r_end = min(a.G0, r_begin + a.regions_per_cta);
+  for (int r = r_begin + warp; r < r_end; r += 8) {
+    const int len = __ldg(a.region_len + r);
+    for (int c = 0; c < a.nKc; ++c) {
+      const float* __restrict__ tab = a.tab + ((size_t)r * a.nKc + c) * a.dim * ROWP;
+      const float* __restrict__ cdt = a.cd + ((size_t)r * a.nKc + c) * a.dim * KC;
+      float val[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) val[k] = 0.f;
+      for (int d = 0; d < len; ++d) {
+        const int f = __float_as_int(__ldg(tab + (size_t)d * ROWP));
+        const float xv = (b < a.B) ? __ldg(a.x + b * a.D + f) : 0.f;
+        float p[NPK], qd[KC];
+        load_row<NPK>(tab + (size_t)d * ROWP + 4, p);
+        load_row<KC>(cdt + (size_t)d * KC, qd);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          float term;
+          if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
+            const float t = fmaf(xv, p[k], p[KC + k]);
+            term = fmaf(-0.5f * t, t, qd[k]);
+          } else {
+            term = fmaf(xv, p[k], qd[k]);
+          }
+          val[k] += nan_to_num(term);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int kk = c * KC + k;
+        if (kk < a.K && b < a.Bp) a.out[((size_t)r * a.K + kk) * a.Bp + b] = val[k];
       }
     }
   }
@@ -455,54 +592,66 @@ __global__ void transpose_to_batch_major(const float* __restrict__ in, float* __
 // =================================================================================================
 // Host-side launchers
 // =================================================================================================
-template <int KC, int ST, int KIND, bool STAGE>
-static int launch_leaf_t(const LeafArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = ratspn_leaf_kernel<KC, ST, KIND, STAGE>;
-  if (smem > 48 * 1024)
-    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+struct LeafLaunch {
+  int mode;      // 2: 64-sample tile, 1: 32-sample tile, 0: wide fallback
+  dim3 grid;
+  size_t smem;
+};
+
+template <int KC, int KIND>
+static int launch_leaf_k(const LeafArgs& a, const LeafLaunch& L, cudaStream_t st) {
   ProfScope prof(CAT_LEAF, st);
-  kern<<<grid, 256, smem, st>>>(a);
+  if (L.mode == 2) {
+    auto kern = ratspn_leaf_kernel<KC, 2, KIND>;
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    kern<<<L.grid, 256, L.smem, st>>>(a);
+  } else if (L.mode == 1) {
+    auto kern = ratspn_leaf_kernel<KC, 1, KIND>;
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    kern<<<L.grid, 256, L.smem, st>>>(a);
+  } else {
+    ratspn_leaf_wide_kernel<KC, KIND><<<L.grid, 256, 0, st>>>(a);
+  }
   DPK_LAUNCH_CHECK("ratspn_leaf_kernel");
   return DPK_OK;
 }
 
-template <int KC, int KIND>
-static int launch_leaf_k(const LeafArgs& a, int st_mode, dim3 grid, size_t smem, cudaStream_t st) {
-  switch (st_mode) {
-    case 2: return launch_leaf_t<KC, 2, KIND, true>(a, grid, smem, st);
-    case 1: return launch_leaf_t<KC, 1, KIND, true>(a, grid, smem, st);
-    default: return launch_leaf_t<KC, 1, KIND, false>(a, grid, 0, st);
-  }
-}
-
 template <int KIND>
-static int launch_leaf_kind(int KC, const LeafArgs& a, int st_mode, dim3 grid, size_t smem, cudaStream_t st) {
+static int launch_leaf_kind(int KC, const LeafArgs& a, const LeafLaunch& L, cudaStream_t st) {
   switch (KC) {
-    case 2: return launch_leaf_k<2, KIND>(a, st_mode, grid, smem, st);
-    case 4: return launch_leaf_k<4, KIND>(a, st_mode, grid, smem, st);
-    case 8: return launch_leaf_k<8, KIND>(a, st_mode, grid, smem, st);
-    case 10: return launch_leaf_k<10, KIND>(a, st_mode, grid, smem, st);
-    case 16: return launch_leaf_k<16, KIND>(a, st_mode, grid, smem, st);
+    case 2: return launch_leaf_k<2, KIND>(a, L, st);
+    case 4: return launch_leaf_k<4, KIND>(a, L, st);
+    case 8: return launch_leaf_k<8, KIND>(a, L, st);
+    case 10: return launch_leaf_k<10, KIND>(a, L, st);
+    case 16: return launch_leaf_k<16, KIND>(a, L, st);
   }
   return set_error(DPK_E_ARG, "unsupported leaf channel chunk %d", KC);
+}
+
+static int run_prep_leaf(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st) {
+  const int64_t total = (int64_t)p.G0 * p.kc.padded * p.dim;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
+  if (p.kind == DPK_LEAF_GAUSSIAN)
+    ratspn_prep_leaf_kernel<DPK_LEAF_GAUSSIAN><<<blocks, 256, 0, st>>>(d->leaf_p0, d->leaf_p1, d->mask, d->region_len,
+                                                                        p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, p.rowp,
+                                                                        ws + p.off_tab, ws + p.off_cd);
+  else
+    ratspn_prep_leaf_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(d->leaf_p0, nullptr, d->mask, d->region_len,
+                                                                         p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, p.rowp,
+                                                                         ws + p.off_tab, ws + p.off_cd);
+  DPK_LAUNCH_CHECK("ratspn_prep_leaf_kernel");
+  const int n = p.G0 * p.kc.padded;
+  ratspn_prep_const_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws + p.off_cd, d->region_len, p.G0, p.dim, p.kc.chunk,
+                                                             p.kc.count, ws + p.off_cst);
+  DPK_LAUNCH_CHECK("ratspn_prep_const_kernel");
+  return DPK_OK;
 }
 
 int ratspn_run_prep(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st) {
   ProfScope prof(CAT_PREP, st, 3 + p.n_sum);
   {
-    const int64_t total = (int64_t)p.G0 * p.kc.padded * p.dim;
-    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
-    if (p.kind == DPK_LEAF_GAUSSIAN)
-      ratspn_prep_leaf_kernel<DPK_LEAF_GAUSSIAN><<<blocks, 256, 0, st>>>(
-          d->leaf_p0, d->leaf_p1, d->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
-    else
-      ratspn_prep_leaf_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(
-          d->leaf_p0, nullptr, d->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
-    DPK_LAUNCH_CHECK("ratspn_prep_leaf_kernel");
-    const int n = p.G0 * p.kc.padded;
-    ratspn_prep_const_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws + p.off_cd, d->region_len, p.G0, p.dim, p.kc.chunk,
-                                                               p.kc.count, ws + p.off_cst);
-    DPK_LAUNCH_CHECK("ratspn_prep_const_kernel");
+    int rc = run_prep_leaf(d, p, ws, st);
+    if (rc) return rc;
   }
   for (int e = 0; e < p.n_sum; ++e) {
     const int P = p.act_regions[e] / 2, kin2 = p.act_ch[e] * p.act_ch[e];
@@ -521,25 +670,34 @@ int ratspn_run_prep(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaS
 
 int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, float* ws, cudaStream_t st) {
   LeafArgs a;
-  a.x = x; a.mask = d->mask; a.region_len = d->region_len;
+  a.x = x; a.region_len = d->region_len;
   a.tab = ws + p.off_tab; a.cd = ws + p.off_cd; a.cst = ws + p.off_cst; a.out = ws + p.off_act[0];
   a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
   const size_t smem_max = (size_t)max_dynamic_smem();
   const int nsm = sm_count();
-  // tile of 64 samples when it fits and there are enough tiles to fill the machine, else 32, else unstaged
-  int st_mode = 0;
-  if ((size_t)p.D * 64 * 4 <= smem_max && ceil_div(p.B, 64) >= nsm) st_mode = 2;
-  else if ((size_t)p.D * 32 * 4 <= smem_max) st_mode = 1;
-  const int TB = (st_mode == 2) ? 64 : 32;
+  const size_t row_bytes = (size_t)p.rowp * 4;
+  // shared memory = x tile + 8 warps x kLeafStages x CH table rows + mbarriers
+  auto ring_rows = [&](int TB) -> int {
+    const size_t fixed = (size_t)p.D * TB * 4 + 8 * kLeafStages * 8 + 128;
+    if (fixed + 8 * kLeafStages * row_bytes > smem_max) return 0;
+    const size_t ch = (smem_max - fixed) / (8 * kLeafStages * row_bytes);
+    return (int)std::min<size_t>(ch, (size_t)std::min(p.dim, 32));
+  };
+  LeafLaunch L;
+  const int ch64 = ring_rows(64), ch32 = ring_rows(32);
+  if (ch64 >= 4 && ceil_div(p.B, 64) >= nsm) { L.mode = 2; a.ring_rows = ch64; }
+  else if (ch32 >= 1) { L.mode = 1; a.ring_rows = ch32; }
+  else { L.mode = 0; a.ring_rows = 0; }
+  const int TB = (L.mode == 2) ? 64 : 32;
   const int64_t ntiles = ceil_div(p.B, TB);
   // split the regions over blockIdx.y only when the batch alone cannot fill the SMs
   int rsplit = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(2 * nsm, ntiles)), ceil_div(p.G0, 8));
   a.regions_per_cta = (int)ceil_div(p.G0, rsplit);
   rsplit = (int)ceil_div(p.G0, a.regions_per_cta);
-  dim3 grid((unsigned)ntiles, (unsigned)rsplit);
-  const size_t smem = st_mode ? (size_t)p.D * TB * 4 : 0;
-  if (p.kind == DPK_LEAF_GAUSSIAN) return launch_leaf_kind<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, st_mode, grid, smem, st);
-  return launch_leaf_kind<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, st_mode, grid, smem, st);
+  L.grid = dim3((unsigned)ntiles, (unsigned)rsplit);
+  L.smem = L.mode ? (size_t)p.D * TB * 4 + (size_t)8 * kLeafStages * a.ring_rows * row_bytes + 8 * kLeafStages * 8 : 0;
+  if (p.kind == DPK_LEAF_GAUSSIAN) return launch_leaf_kind<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, L, st);
+  return launch_leaf_kind<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, L, st);
 }
 
 template <int OC, int ST, bool ROOT>
@@ -563,7 +721,9 @@ static int launch_einsum(EinsumArgs a, int OC, cudaStream_t st) {
   const size_t wbytes = (size_t)rows * a.Kin * OC * 4;
   int ST = 4;
   size_t smem = 2 * (size_t)a.Kin * kEinsumThreads * ST * 4 + wbytes;
-  if (smem > 100 * 1024 || a.Bp < 4 * kEinsumThreads) { ST = 1; smem = 2 * (size_t)a.Kin * kEinsumThreads * 4 + wbytes; }
+  // 4 samples per thread amortise the weight broadcasts; fall back to 1 when that would leave SMs idle
+  const int64_t ctas4 = ceil_div(a.Bp, 4 * kEinsumThreads) * (ROOT ? 1 : a.P);
+  if (smem > 100 * 1024 || ctas4 < 2 * sm_count()) { ST = 1; smem = 2 * (size_t)a.Kin * kEinsumThreads * 4 + wbytes; }
   if (smem > smem_max) return set_error(DPK_E_ARG, "einsum level with %d inputs per region does not fit shared memory", a.Kin);
   dim3 grid((unsigned)ceil_div(a.Bp, kEinsumThreads * ST), ROOT ? 1u : (unsigned)a.P);
 #define DPK_EINSUM_CASE(oc)                                                             \
@@ -646,19 +806,7 @@ extern "C" int dpk_ratspn_leaf_forward(const dpk_ratspn_desc* desc, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     ProfScope prof(CAT_PREP, st, 2);
-    const int64_t total = (int64_t)p.G0 * p.kc.padded * p.dim;
-    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
-    if (p.kind == DPK_LEAF_GAUSSIAN)
-      ratspn_prep_leaf_kernel<DPK_LEAF_GAUSSIAN><<<blocks, 256, 0, st>>>(
-          desc->leaf_p0, desc->leaf_p1, desc->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
-    else
-      ratspn_prep_leaf_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(
-          desc->leaf_p0, nullptr, desc->region_len, p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, ws + p.off_tab, ws + p.off_cd);
-    DPK_LAUNCH_CHECK("ratspn_prep_leaf_kernel");
-    const int n = p.G0 * p.kc.padded;
-    ratspn_prep_const_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws + p.off_cd, desc->region_len, p.G0, p.dim, p.kc.chunk,
-                                                               p.kc.count, ws + p.off_cst);
-    DPK_LAUNCH_CHECK("ratspn_prep_const_kernel");
+    if ((rc = run_prep_leaf(desc, p, ws, st))) return rc;
   }
   if ((rc = ratspn_run_leaf(desc, p, x, ws, st))) return rc;
   const int rows = p.G0 * p.K;

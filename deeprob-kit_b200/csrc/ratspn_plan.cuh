@@ -5,7 +5,8 @@
 namespace dpk {
 
 // Workspace layout (all offsets in floats, each 256-byte aligned):
-//   leaf tables   tab   [G0][nKc][dim][NP*KC]   (Gaussian NP=2: 1/sigma | -mu/sigma ; Bernoulli NP=1: logit)
+//   leaf tables   tab   [G0][nKc][dim][ROWP]    row = {feature index (int bits), 0, 0, 0, NP*KC values}
+//                                              (Gaussian NP=2: 1/sigma[KC] | -mu/sigma[KC]; Bernoulli NP=1: logit[KC])
 //                 cd    [G0][nKc][dim][KC]      per-dim additive constant (-log sigma - log sqrt(2pi) | -softplus)
 //                 cst   [G0][Kp]                sum over the real dims of cd
 //   sum level e   wsoft/wlog [P_e][nOc][Kin_e^2][OC]   softmax / log-softmax of the raw logits
@@ -17,7 +18,8 @@ struct RatPlan {
   int n_sum;  // depth - 1 inner sum levels
   int64_t B, Bp;
   Chunking kc, oc, cc;
-  int np;  // table values per channel on the fast path
+  int np;    // table values per channel on the fast path
+  int rowp;  // floats per table row: 4 (feature index + pad) + round_up(np * KC, 4)
   int act_regions[DPK_MAX_LEVELS], act_ch[DPK_MAX_LEVELS];
   size_t off_tab, off_cd, off_cst;
   size_t off_wsoft[DPK_MAX_LEVELS], off_wlog[DPK_MAX_LEVELS], w_floats[DPK_MAX_LEVELS];
@@ -51,7 +53,8 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
   p->np = (p->kind == DPK_LEAF_GAUSSIAN) ? 2 : 1;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = align64(off + n); return o; };
-  p->off_tab = take((size_t)p->G0 * p->kc.count * p->dim * p->np * p->kc.chunk);
+  p->rowp = 4 + (p->np * p->kc.chunk + 3) / 4 * 4;
+  p->off_tab = take((size_t)p->G0 * p->kc.count * p->dim * p->rowp);
   p->off_cd = take((size_t)p->G0 * p->kc.count * p->dim * p->kc.chunk);
   p->off_cst = take((size_t)p->G0 * p->kc.padded);
   for (int l = 0; l < p->depth; ++l) {

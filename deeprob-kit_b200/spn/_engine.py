@@ -121,7 +121,7 @@ class _RatSpnLogProb(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, *params):
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need_grad = any(ctx.needs_input_grad)   # False under no_grad / when nothing requires grad
         call = model._make_call(x.device)
         batch = x.shape[0]
         flags = _lib.F_SAVE_ACTIVATIONS if need_grad else 0

@@ -153,6 +153,13 @@ class RatSpnOracle:
 
     clean_nan = False   # see leaf_layer
 
+    def double(self) -> "RatSpnOracle":
+        """Same model in float64 (ground truth for gradient comparisons)."""
+        self.params = {k: v.double() for k, v in self.params.items()}
+        self.sum_weights = [w.double() for w in self.sum_weights]
+        self.root_weight = self.root_weight.double()
+        return self
+
     def leaf(self, x):
         return leaf_layer(x, self.mask, self.pad_mask, self.kind, self.params, self.clean_nan)
 
@@ -224,7 +231,7 @@ class RatSpnOracle:
         if self.pad_mask is not None:
             ok = ok & ~self.pad_mask[:, 0, :].unsqueeze(0)
         v0 = torch.where(ok, v, torch.zeros_like(v))
-        okf = ok.float()
+        okf = ok.to(post.dtype)
         s0 = torch.einsum("bgk,bgd->gkd", post, okf)
         s1 = torch.einsum("bgk,bgd->gkd", post, v0)
         s2 = torch.einsum("bgk,bgd->gkd", post, v0 * v0)
