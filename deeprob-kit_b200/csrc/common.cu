@@ -26,7 +26,7 @@ static DevAttr& attr() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     a.sms = sms > 0 ? sms : 148;
-    a.smem = smem > 0 ? smem : 48 * 1024;
+    a.smem = smem > 0 ? smem : 232448;  // no device (host-only planning): B200 opt-in limit
     a.ok = true;  // benign race: every thread writes the same values
   }
   return a;

@@ -352,7 +352,7 @@ __global__ void ratspn_leaf_finalize_kernel(const float* __restrict__ p0, const 
       continue;
     }
     if (KIND == DPK_LEAF_GAUSSIAN) {
-      const float mu = p0[idx], sg = p1[idx], S2 = s2[idx];
+      const float mu = p0[idx], sg = p1 ? p1[idx] : 1.0f, S2 = s2[idx];
       const float inv = 1.0f / sg, inv2 = inv * inv;
       if (o0) o0[idx] += (S1 - mu * S0) * inv2;
       if (o1) o1[idx] += (S2 - 2.0f * mu * S1 + mu * mu * S0) * inv2 * inv - S0 * inv;
@@ -371,7 +371,8 @@ struct LeafBwdXArgs {
   const float* x;
   const int32_t* mask;
   const int32_t* region_len;
-  const float* tab;  // forward table [G0][nKc][dim][ROWP]
+  const float* tab;  // forward table (chunked layout, see ratspn_plan.cuh)
+  int CH, NCH, CHP, CF;
   const float* g0;   // [G0][K][Bp]
   float* gx;         // (B, D), accumulated
   int64_t B, Bp;
@@ -381,9 +382,8 @@ struct LeafBwdXArgs {
 template <int KC, int KIND, bool STAGE>
 __global__ void __launch_bounds__(256) ratspn_leaf_bwd_x_kernel(const LeafBwdXArgs a) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;
+  constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;   // KIND may also be kLeafGaussUnit (scale == 1)
   constexpr int NPK = (NP * KC + 3) / 4 * 4;
-  constexpr int ROW = 4 + NPK;          // table row: {feature index, pad x3, values}
   float* xs = sm;                       // [D][32] swizzled
   float* gxs = sm + (size_t)a.D * 32;   // [D][32] swizzled
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -411,20 +411,23 @@ __global__ void __launch_bounds__(256) ratspn_leaf_bwd_x_kernel(const LeafBwdXAr
         const int kk = c * KC + k;
         g[k] = (kk < a.K && b < a.B) ? a.g0[((size_t)r * a.K + kk) * a.Bp + b] : 0.f;
       }
-      const float* __restrict__ tab = a.tab + ((size_t)r * a.nKc + c) * a.dim * ROW;
+      const float* __restrict__ block = a.tab + ((size_t)r * a.nKc + c) * a.NCH * a.CF;
       for (int d = 0; d < len; ++d) {
         const int ff = __ldg(m + d);
         float xv;
         if constexpr (STAGE) xv = xs[ff * 32 + (lane ^ (ff & 31))];
         else xv = (b < a.B) ? __ldg(a.x + b * a.D + ff) : 0.f;
         float p[NPK];
-        load_row<NPK>(tab + (size_t)d * ROW + 4, p);
+        const int chk = d / a.CH;
+        load_row<NPK>(block + (size_t)chk * a.CF + a.CHP + (d - chk * a.CH) * NPK, p);
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
           if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
             const float t = fmaf(xv, p[k], p[KC + k]);   // (x - mu) / sigma
             acc = fmaf(g[k], -t * p[k], acc);            // d/dx of -t^2/2
+          } else if constexpr (KIND == kLeafGaussUnit) {
+            acc = fmaf(g[k], -(xv + p[k]), acc);         // sigma == 1
           } else {
             acc = fmaf(g[k], p[k], acc);                 // d/dx of x*logit - softplus
           }
@@ -620,8 +623,10 @@ static int run_backward(const dpk_ratspn_desc* d, const RatPlan& p, const float*
     LeafBwdXArgs a;
     a.x = x; a.mask = d->mask; a.region_len = d->region_len; a.tab = ws + p.off_tab; a.g0 = ws + p.off_gact[0];
     a.gx = t.gx; a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
-    int rc = (p.kind == DPK_LEAF_GAUSSIAN) ? launch_leaf_x<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, st)
-                                           : launch_leaf_x<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, st);
+    a.CH = p.leaf_ch; a.NCH = p.leaf_nch; a.CHP = p.leaf_chp; a.CF = p.leaf_chunk_floats;
+    int rc = (p.fwd_kind == DPK_LEAF_GAUSSIAN) ? launch_leaf_x<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, st)
+             : (p.fwd_kind == kLeafGaussUnit)  ? launch_leaf_x<kLeafGaussUnit>(p.kc.chunk, a, st)
+                                               : launch_leaf_x<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, st);
     if (rc) return rc;
   }
   return DPK_OK;

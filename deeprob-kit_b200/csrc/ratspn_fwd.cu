@@ -21,49 +21,63 @@ namespace dpk {
 // =================================================================================================
 // Parameter preparation (tiny; re-run every call because the optimiser updates parameters in place)
 // =================================================================================================
+struct LeafTabGeom {
+  int CH, NCH, CHP, NPK, CF, TB, NST;  // see RatPlan::leaf_*
+};
+
+// parameters of table row d of a (region, channel-chunk) block
+__device__ __forceinline__ const float* leaf_tab_row(const float* block, int d, const LeafTabGeom& g) {
+  const int ch = d / g.CH;
+  return block + (size_t)ch * g.CF + g.CHP + (d - ch * g.CH) * g.NPK;
+}
+
 template <int KIND>
 __global__ void ratspn_prep_leaf_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
                                         const int32_t* __restrict__ mask, const int32_t* __restrict__ region_len,
-                                        int G0, int K, int dim, int KC, int nKc, int rowp,
+                                        int G0, int K, int dim, int KC, int nKc, LeafTabGeom g,
                                         float* __restrict__ tab, float* __restrict__ cd) {
   const int Kp = KC * nKc;
-  const int64_t total = (int64_t)G0 * Kp * dim;
+  const int dimp = g.NCH * g.CH;  // rows incl. the padding of the last chunk
+  const int64_t total = (int64_t)G0 * Kp * dimp;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(idx % dim);
-    const int kk = (int)((idx / dim) % Kp);
-    const int g = (int)(idx / ((int64_t)dim * Kp));
+    const int d = (int)(idx % dimp);
+    const int kk = (int)((idx / dimp) % Kp);
+    const int r = (int)(idx / ((int64_t)dimp * Kp));
     const int c = kk / KC, k = kk % KC;
-    const bool live = kk < K && d < region_len[g];   // pad dims / pad channels contribute exactly 0
-    const size_t src = ((size_t)g * K + kk) * dim + d;
-    const size_t row = ((size_t)g * nKc + c) * dim + d;
-    float* trow = tab + row * rowp;
+    const bool live = kk < K && d < region_len[r];   // pad dims / pad channels contribute exactly 0
+    const size_t src = ((size_t)r * K + kk) * dim + d;
+    const int ch = d / g.CH, w = d - ch * g.CH;
+    float* chunk = tab + (((size_t)r * nKc + c) * g.NCH + ch) * g.CF;
+    float* trow = chunk + g.CHP + w * g.NPK;
     if (k == 0) {
-      trow[0] = __int_as_float(mask[(size_t)g * dim + d]);
-      trow[1] = 0.f; trow[2] = 0.f; trow[3] = 0.f;
-      const int used = 4 + ((KIND == DPK_LEAF_GAUSSIAN) ? 2 * KC : KC);
-      for (int z = used; z < rowp; ++z) trow[z] = 0.f;
+      const int f = (d < dim) ? mask[(size_t)r * dim + d] : 0;
+      chunk[w] = __uint_as_float((uint32_t)f * (uint32_t)g.TB * 4u + ((uint32_t)f & 31u) * 4u);
+      if (w == 0) for (int z = g.CH; z < g.CHP; ++z) chunk[z] = 0.f;
+      const int used = (KIND == DPK_LEAF_GAUSSIAN) ? 2 * KC : KC;
+      for (int z = used; z < g.NPK; ++z) trow[z] = 0.f;
     }
-    if (KIND == DPK_LEAF_GAUSSIAN) {
-      float rs = 0.f, mr = 0.f, cdv = 0.f;
+    float v0 = 0.f, v1 = 0.f, cdv = 0.f;
+    if (KIND == kLeafGaussUnit) {
+      if (live) { v0 = -p0[src]; cdv = -kLogSqrt2Pi; }   // scale == 1: t = x - mu
+      trow[k] = v0;
+    } else if (KIND == DPK_LEAF_GAUSSIAN) {
       if (live) {
         const float sigma = p1[src], mu = p0[src];
-        rs = 1.0f / sigma;
-        mr = -mu * rs;
+        v0 = 1.0f / sigma;
+        v1 = -mu * v0;
         cdv = -logf(sigma) - kLogSqrt2Pi;
       }
-      trow[4 + k] = rs;
-      trow[4 + KC + k] = mr;
-      cd[row * KC + k] = cdv;
+      trow[k] = v0;
+      trow[KC + k] = v1;
     } else {
-      float lg = 0.f, cdv = 0.f;
       if (live) {
-        lg = p0[src];
-        cdv = -(fmaxf(lg, 0.f) + log1pf(expf(-fabsf(lg))));  // -softplus(logit)
+        v0 = p0[src];
+        cdv = -(fmaxf(v0, 0.f) + log1pf(expf(-fabsf(v0))));  // -softplus(logit)
       }
-      trow[4 + k] = lg;
-      cd[row * KC + k] = cdv;
+      trow[k] = v0;
     }
+    if (d < dim) cd[(((size_t)r * nKc + c) * dim + d) * KC + k] = cdv;
   }
 }
 
@@ -136,17 +150,16 @@ __global__ void ratspn_prep_weight_kernel(const float* __restrict__ src, int mod
 // =================================================================================================
 struct LeafArgs {
   const float* x;            // (B, D)
+  const int32_t* mask;       // (G0, dim)
   const int32_t* region_len; // (G0)
-  const float* tab;          // [G0][nKc][dim][ROWP]
+  const float* tab;          // chunked table, see ratspn_plan.cuh
   const float* cd;           // [G0][nKc][dim][KC]
   const float* cst;          // [G0][Kp]
   float* out;                // [G0][K][Bp]
   int64_t B, Bp;
   int D, G0, K, dim, nKc, regions_per_cta;
-  int ring_rows;             // CH: table rows per ring stage
+  LeafTabGeom g;
 };
-
-constexpr int kLeafStages = 4;  // per-warp ring depth of TMA-bulk parameter chunks
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -181,62 +194,74 @@ __device__ __forceinline__ void cp_async_4(void* dst, const void* src, uint32_t 
 //      element (feature f, sample s) at f*TB + ((s&31) ^ (f&31)) + (s & ~31)
 //    (conflict-free for the fill, lanes = features, and for the sweep, lanes = samples);
 //  * a warp owns one region at a time, lanes = samples, accumulators for ST samples x KC channels
-//    live in registers; the (feature index, 1/sigma, -mu/sigma) rows of the region stream through a
-//    warp-private ring of TMA bulk copies (cp.async.bulk + mbarrier), so the inner loop only issues
-//    warp-uniform (broadcast) shared loads;
-//  * 2 packed FFMA2 per pair of channels and feature:  t = x*rs + mr ; acc += t*t.
+//    live in registers; the (1/sigma, -mu/sigma) rows of the region stream through a warp-private
+//    ring of TMA bulk copies (cp.async.bulk + mbarrier) and are read as warp-uniform broadcasts;
+//    the chunk header holds the pre-swizzled x-tile offset of every row, so the gather address is
+//    one shuffle + one XOR;
+//  * rows are software-pipelined through two register sets so the shared loads of row d+1 overlap
+//    the packed FFMA2 of row d:  t = x*rs + mr ; acc += t*t  (2 FFMA2 per channel pair and feature).
 // A non-finite input makes the fast result non-finite; that is detected per region and the region is
 // redone on the exact path, which applies nan_to_num term by term like ratspn.py:103.
+template <int KIND>
+__device__ __forceinline__ float leaf_term(float xv, float p0, float p1, float cd) {
+  if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
+    const float t = fmaf(xv, p0, p1);
+    return fmaf(-0.5f * t, t, cd);
+  } else if constexpr (KIND == kLeafGaussUnit) {
+    const float t = xv + p0;
+    return fmaf(-0.5f * t, t, cd);
+  } else {
+    return fmaf(xv, p0, cd);
+  }
+}
+
 template <int KC, int ST, int KIND>
 __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int TB = 32 * ST;
   constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;
   constexpr int NPK = (NP * KC + 3) / 4 * 4;
-  constexpr int ROWP = 4 + NPK;
   constexpr int KH = KC / 2;
+  constexpr bool QUAD = (KIND != DPK_LEAF_BERNOULLI);   // quadratic (Gaussian) vs linear (Bernoulli) term
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * TB;
-  const int CH = a.ring_rows;
+  const int CH = a.g.CH, NCH = a.g.NCH, CHP = a.g.CHP, CF = a.g.CF, NST = a.g.NST;
 
   float* xs = reinterpret_cast<float*>(smem_raw);
-  float* ring = xs + (size_t)a.D * TB + (size_t)warp * kLeafStages * CH * ROWP;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xs + (size_t)a.D * TB + (size_t)8 * kLeafStages * CH * ROWP) +
-                   warp * kLeafStages;
+  float* ring = xs + (size_t)a.D * TB + (size_t)warp * NST * CF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xs + (size_t)a.D * TB + (size_t)kLeafWarps * NST * CF) +
+                   warp * kLeafMaxStages;
 
-  // ---- this warp's work list: regions r_begin+warp, +8, ... ; nKc channel chunks each ----------
+  // ---- this warp's work list: regions r_begin+warp, +8, ... ; nKc*NCH chunks each ---------------
   const int r_begin = blockIdx.y * a.regions_per_cta;
   const int r_end = min(a.G0, r_begin + a.regions_per_cta);
-  const int n_reg = (r_end - r_begin - warp + 7) / 8;          // may be <= 0
-  const int NCH = (a.dim + CH - 1) / CH;
-  const int n_chunks = max(n_reg, 0) * a.nKc * NCH;
+  const int n_reg = max(0, (r_end - r_begin - warp + 7) / 8);
+  const int per_region = a.nKc * NCH;
 
   if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kLeafStages; ++s) mbar_init(bars + s, 1);
+    for (int s = 0; s < NST; ++s) mbar_init(bars + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
 
-  // producer cursor (lane 0 issues): chunk q -> (region, channel chunk, row chunk)
-  int pq = 0, p_reg = r_begin + warp, p_c = 0, p_ch = 0;
+  // producer side (lane 0 issues; every lane tracks the cursor so the state stays warp-uniform)
+  const float* p_src = a.tab + (size_t)(r_begin + warp) * per_region * CF;
+  int p_left = n_reg * per_region, p_in_region = 0, p_stage = 0;
+  const uint32_t chunk_bytes = (uint32_t)CF * 4;
   auto issue = [&]() {
-    if (pq < n_chunks) {
+    if (p_left > 0) {
       if (lane == 0) {
-        const int rows = min(CH, a.dim - p_ch * CH);
-        const float* src = a.tab + (((size_t)p_reg * a.nKc + p_c) * a.dim + (size_t)p_ch * CH) * ROWP;
-        const int stage = pq % kLeafStages;
-        const uint32_t bytes = (uint32_t)rows * ROWP * 4;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bars + stage, bytes);
-        bulk_g2s(ring + (size_t)stage * CH * ROWP, src, bytes, bars + stage);
+        mbar_expect_tx(bars + p_stage, chunk_bytes);
+        bulk_g2s(ring + (size_t)p_stage * CF, p_src, chunk_bytes, bars + p_stage);
       }
-      ++pq;
-      if (++p_ch == NCH) { p_ch = 0; if (++p_c == a.nKc) { p_c = 0; p_reg += 8; } }
+      --p_left;
+      p_src += CF;
+      if (++p_in_region == per_region) { p_in_region = 0; p_src += (size_t)(kLeafWarps - 1) * per_region * CF; }
+      p_stage = (p_stage + 1 == NST) ? 0 : p_stage + 1;
     }
   };
-#pragma unroll
-  for (int s = 0; s < kLeafStages - 1; ++s) issue();
+  for (int s = 0; s < NST - 1; ++s) issue();
 
   // ---- x tile: asynchronous transposing fill -------------------------------------------------
   for (int s = warp; s < TB; s += 8) {
@@ -250,7 +275,10 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
   __syncthreads();
 
   // ---- sweep ------------------------------------------------------------------------------------
-  int q = 0;
+  const char* xs_bytes = reinterpret_cast<const char*>(xs);
+  const uint32_t lane_x = (uint32_t)lane << 2;
+  int c_stage = 0;
+  uint32_t c_parity = 0;
   for (int ri = 0; ri < n_reg; ++ri) {
     const int r = r_begin + warp + 8 * ri;
     for (int c = 0; c < a.nKc; ++c) {
@@ -260,36 +288,56 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
 #pragma unroll
         for (int k = 0; k < KH; ++k) acc[s][k] = make_float2(0.f, 0.f);
 
-      for (int ch = 0; ch < NCH; ++ch, ++q) {
-        issue();                                         // keep kLeafStages-1 chunks in flight
-        const int stage = q % kLeafStages;
-        mbar_wait(bars + stage, (q / kLeafStages) & 1);
-        const float* __restrict__ rows = ring + (size_t)stage * CH * ROWP;
+      for (int ch = 0; ch < NCH; ++ch) {
+        issue();                                         // keep NST-1 chunks in flight
+        mbar_wait(bars + c_stage, c_parity);
+        const float* __restrict__ chunk = ring + (size_t)c_stage * CF;
+        const uint32_t* __restrict__ hdr = reinterpret_cast<const uint32_t*>(chunk);
+        const float* __restrict__ rows = chunk + CHP;
         const int nrows = min(CH, a.dim - ch * CH);
-#pragma unroll 2
-        for (int d = 0; d < nrows; ++d) {
-          const float4 head = *reinterpret_cast<const float4*>(rows + d * ROWP);
-          const int f = __float_as_int(head.x);
-          float p[NPK];
-          load_row_smem<NPK>(rows + d * ROWP + 4, p);
-          const int at = f * TB + (lane ^ (f & 31));
+
+        // Software pipeline, per row d: header word fetched 2 rows ahead, x + parameters 1 row ahead,
+        // so that no shared-memory latency sits between the FFMA2 blocks of consecutive rows.
+        auto load_row_regs = [&](int d, uint32_t h, float (&p)[NPK], float (&xv)[ST]) {
+          const float* xp = reinterpret_cast<const float*>(xs_bytes + (h ^ lane_x));
+#pragma unroll
+          for (int s = 0; s < ST; ++s) xv[s] = xp[32 * s];
+          load_row_smem<NPK>(rows + d * NPK, p);
+        };
+        auto fma_row = [&](const float (&p)[NPK], const float (&xv)[ST]) {
 #pragma unroll
           for (int s = 0; s < ST; ++s) {
-            const float xv = xs[at + 32 * s];
-            const float2 x2 = make_float2(xv, xv);
+            const float2 x2 = make_float2(xv[s], xv[s]);
 #pragma unroll
             for (int k = 0; k < KH; ++k) {
+              const float2 p0 = make_float2(p[2 * k], p[2 * k + 1]);
               if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
-                const float2 t = __ffma2_rn(x2, make_float2(p[2 * k], p[2 * k + 1]),
-                                            make_float2(p[KC + 2 * k], p[KC + 2 * k + 1]));
+                const float2 t = __ffma2_rn(x2, p0, make_float2(p[KC + 2 * k], p[KC + 2 * k + 1]));
+                acc[s][k] = __ffma2_rn(t, t, acc[s][k]);
+              } else if constexpr (KIND == kLeafGaussUnit) {
+                const float2 t = __fadd2_rn(x2, p0);
                 acc[s][k] = __ffma2_rn(t, t, acc[s][k]);
               } else {
-                acc[s][k] = __ffma2_rn(x2, make_float2(p[2 * k], p[2 * k + 1]), acc[s][k]);
+                acc[s][k] = __ffma2_rn(x2, p0, acc[s][k]);
               }
             }
           }
+        };
+        float pA[NPK], pB[NPK], xA[ST], xB[ST];
+        uint32_t h1 = hdr[nrows > 1 ? 1 : 0];
+        load_row_regs(0, hdr[0], pA, xA);
+        int d = 0;
+        for (; d + 2 <= nrows; d += 2) {
+          const uint32_t h2 = hdr[d + 2 < nrows ? d + 2 : d];
+          load_row_regs(d + 1, h1, pB, xB);
+          fma_row(pA, xA);
+          h1 = hdr[d + 3 < nrows ? d + 3 : d];
+          if (d + 2 < nrows) load_row_regs(d + 2, h2, pA, xA);
+          fma_row(pB, xB);
         }
+        if (d < nrows) fma_row(pA, xA);
         __syncwarp();                                    // every lane is done with this stage
+        if (++c_stage == NST) { c_stage = 0; c_parity ^= 1u; }
       }
 
       // ---- finish the (region, channel chunk): constants, non-finite check, store -------------
@@ -302,38 +350,31 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
 #pragma unroll
         for (int s = 0; s < ST; ++s) {
           const float av = (k & 1) ? acc[s][k / 2].y : acc[s][k / 2].x;
-          val[s][k] = (KIND == DPK_LEAF_GAUSSIAN) ? fmaf(-0.5f, av, cv) : av + cv;
+          val[s][k] = QUAD ? fmaf(-0.5f, av, cv) : av + cv;
           bad |= !(fabsf(val[s][k]) <= FLT_MAX);
         }
       }
       if (__any_sync(0xffffffffu, bad)) {
         // exact path for this region: every term goes through nan_to_num like ratspn.py:103
-        const float* __restrict__ tab = a.tab + ((size_t)r * a.nKc + c) * a.dim * ROWP;
+        const float* __restrict__ block = a.tab + ((size_t)r * a.nKc + c) * NCH * CF;
         const float* __restrict__ cdt = a.cd + ((size_t)r * a.nKc + c) * a.dim * KC;
+        const int32_t* __restrict__ m = a.mask + (size_t)r * a.dim;
         const int len = __ldg(a.region_len + r);
 #pragma unroll
         for (int s = 0; s < ST; ++s)
 #pragma unroll
           for (int k = 0; k < KC; ++k) val[s][k] = 0.f;
         for (int d = 0; d < len; ++d) {
-          const int f = __float_as_int(__ldg(tab + (size_t)d * ROWP));
+          const int f = __ldg(m + d);
           float p[NPK], qd[KC];
-          load_row<NPK>(tab + (size_t)d * ROWP + 4, p);
+          load_row<NPK>(leaf_tab_row(block, d, a.g), p);
           load_row<KC>(cdt + (size_t)d * KC, qd);
 #pragma unroll
           for (int s = 0; s < ST; ++s) {
             const float xv = xs[f * TB + (lane ^ (f & 31)) + 32 * s];
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-              float term;
-              if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
-                const float t = fmaf(xv, p[k], p[KC + k]);
-                term = fmaf(-0.5f * t, t, qd[k]);
-              } else {
-                term = fmaf(xv, p[k], qd[k]);
-              }
-              val[s][k] += nan_to_num(term);
-            }
+            for (int k = 0; k < KC; ++k)
+              val[s][k] += nan_to_num(leaf_term<KIND>(xv, p[k], NP == 2 ? p[KC + k] : 0.f, qd[k]));
           }
         }
       }
@@ -355,36 +396,28 @@ template <int KC, int KIND>
 __global__ void __launch_bounds__(256) ratspn_leaf_wide_kernel(const LeafArgs a) {
   constexpr int NP = (KIND == DPK_LEAF_GAUSSIAN) ? 2 : 1;
   constexpr int NPK = (NP * KC + 3) / 4 * 4;
-  constexpr int ROWP = 4 + NPK;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * 32 + lane;
   const int r_begin = blockIdx.y * a.regions_per_cta;
   const int r_end = min(a.G0, r_begin + a.regions_per_cta);
   for (int r = r_begin + warp; r < r_end; r += 8) {
     const int len = __ldg(a.region_len + r);
+    const int32_t* __restrict__ m = a.mask + (size_t)r * a.dim;
     for (int c = 0; c < a.nKc; ++c) {
-      const float* __restrict__ tab = a.tab + ((size_t)r * a.nKc + c) * a.dim * ROWP;
+      const float* __restrict__ block = a.tab + ((size_t)r * a.nKc + c) * a.g.NCH * a.g.CF;
       const float* __restrict__ cdt = a.cd + ((size_t)r * a.nKc + c) * a.dim * KC;
       float val[KC];
 #pragma unroll
       for (int k = 0; k < KC; ++k) val[k] = 0.f;
       for (int d = 0; d < len; ++d) {
-        const int f = __float_as_int(__ldg(tab + (size_t)d * ROWP));
+        const int f = __ldg(m + d);
         const float xv = (b < a.B) ? __ldg(a.x + b * a.D + f) : 0.f;
         float p[NPK], qd[KC];
-        load_row<NPK>(tab + (size_t)d * ROWP + 4, p);
+        load_row<NPK>(leaf_tab_row(block, d, a.g), p);
         load_row<KC>(cdt + (size_t)d * KC, qd);
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
-          float term;
-          if constexpr (KIND == DPK_LEAF_GAUSSIAN) {
-            const float t = fmaf(xv, p[k], p[KC + k]);
-            term = fmaf(-0.5f * t, t, qd[k]);
-          } else {
-            term = fmaf(xv, p[k], qd[k]);
-          }
-          val[k] += nan_to_num(term);
-        }
+        for (int k = 0; k < KC; ++k)
+          val[k] += nan_to_num(leaf_term<KIND>(xv, p[k], NP == 2 ? p[KC + k] : 0.f, qd[k]));
       }
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
@@ -628,17 +661,27 @@ static int launch_leaf_kind(int KC, const LeafArgs& a, const LeafLaunch& L, cuda
   return set_error(DPK_E_ARG, "unsupported leaf channel chunk %d", KC);
 }
 
+static LeafTabGeom leaf_geom(const RatPlan& p) {
+  LeafTabGeom g;
+  g.CH = p.leaf_ch; g.NCH = p.leaf_nch; g.CHP = p.leaf_chp; g.NPK = p.leaf_npk; g.CF = p.leaf_chunk_floats; g.TB = p.leaf_tb; g.NST = p.leaf_stages;
+  return g;
+}
+
 static int run_prep_leaf(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st) {
-  const int64_t total = (int64_t)p.G0 * p.kc.padded * p.dim;
+  const int64_t total = (int64_t)p.G0 * p.kc.padded * p.leaf_nch * p.leaf_ch;
   const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
-  if (p.kind == DPK_LEAF_GAUSSIAN)
+  if (p.fwd_kind == DPK_LEAF_GAUSSIAN)
     ratspn_prep_leaf_kernel<DPK_LEAF_GAUSSIAN><<<blocks, 256, 0, st>>>(d->leaf_p0, d->leaf_p1, d->mask, d->region_len,
-                                                                        p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, p.rowp,
-                                                                        ws + p.off_tab, ws + p.off_cd);
+                                                                        p.G0, p.K, p.dim, p.kc.chunk, p.kc.count,
+                                                                        leaf_geom(p), ws + p.off_tab, ws + p.off_cd);
+  else if (p.fwd_kind == kLeafGaussUnit)
+    ratspn_prep_leaf_kernel<kLeafGaussUnit><<<blocks, 256, 0, st>>>(d->leaf_p0, nullptr, d->mask, d->region_len,
+                                                                     p.G0, p.K, p.dim, p.kc.chunk, p.kc.count,
+                                                                     leaf_geom(p), ws + p.off_tab, ws + p.off_cd);
   else
     ratspn_prep_leaf_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(d->leaf_p0, nullptr, d->mask, d->region_len,
-                                                                         p.G0, p.K, p.dim, p.kc.chunk, p.kc.count, p.rowp,
-                                                                         ws + p.off_tab, ws + p.off_cd);
+                                                                         p.G0, p.K, p.dim, p.kc.chunk, p.kc.count,
+                                                                         leaf_geom(p), ws + p.off_tab, ws + p.off_cd);
   DPK_LAUNCH_CHECK("ratspn_prep_leaf_kernel");
   const int n = p.G0 * p.kc.padded;
   ratspn_prep_const_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws + p.off_cd, d->region_len, p.G0, p.dim, p.kc.chunk,
@@ -670,33 +713,22 @@ int ratspn_run_prep(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaS
 
 int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, float* ws, cudaStream_t st) {
   LeafArgs a;
-  a.x = x; a.region_len = d->region_len;
+  a.x = x; a.mask = d->mask; a.region_len = d->region_len;
   a.tab = ws + p.off_tab; a.cd = ws + p.off_cd; a.cst = ws + p.off_cst; a.out = ws + p.off_act[0];
   a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
-  const size_t smem_max = (size_t)max_dynamic_smem();
+  a.g = leaf_geom(p);
   const int nsm = sm_count();
-  const size_t row_bytes = (size_t)p.rowp * 4;
-  // shared memory = x tile + 8 warps x kLeafStages x CH table rows + mbarriers
-  auto ring_rows = [&](int TB) -> int {
-    const size_t fixed = (size_t)p.D * TB * 4 + 8 * kLeafStages * 8 + 128;
-    if (fixed + 8 * kLeafStages * row_bytes > smem_max) return 0;
-    const size_t ch = (smem_max - fixed) / (8 * kLeafStages * row_bytes);
-    return (int)std::min<size_t>(ch, (size_t)std::min(p.dim, 32));
-  };
   LeafLaunch L;
-  const int ch64 = ring_rows(64), ch32 = ring_rows(32);
-  if (ch64 >= 4 && ceil_div(p.B, 64) >= nsm) { L.mode = 2; a.ring_rows = ch64; }
-  else if (ch32 >= 1) { L.mode = 1; a.ring_rows = ch32; }
-  else { L.mode = 0; a.ring_rows = 0; }
-  const int TB = (L.mode == 2) ? 64 : 32;
-  const int64_t ntiles = ceil_div(p.B, TB);
+  L.mode = p.leaf_mode;
+  const int64_t ntiles = ceil_div(p.B, p.leaf_tb);
   // split the regions over blockIdx.y only when the batch alone cannot fill the SMs
   int rsplit = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(2 * nsm, ntiles)), ceil_div(p.G0, 8));
-  a.regions_per_cta = (int)ceil_div(p.G0, rsplit);
+  a.regions_per_cta = (int)round_up(ceil_div(p.G0, rsplit), 8);
   rsplit = (int)ceil_div(p.G0, a.regions_per_cta);
   L.grid = dim3((unsigned)ntiles, (unsigned)rsplit);
-  L.smem = L.mode ? (size_t)p.D * TB * 4 + (size_t)8 * kLeafStages * a.ring_rows * row_bytes + 8 * kLeafStages * 8 : 0;
-  if (p.kind == DPK_LEAF_GAUSSIAN) return launch_leaf_kind<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, L, st);
+  L.smem = p.leaf_smem;
+  if (p.fwd_kind == DPK_LEAF_GAUSSIAN) return launch_leaf_kind<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, L, st);
+  if (p.fwd_kind == kLeafGaussUnit) return launch_leaf_kind<kLeafGaussUnit>(p.kc.chunk, a, L, st);
   return launch_leaf_kind<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, L, st);
 }
 
@@ -781,7 +813,7 @@ extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, i
   if (rc) return rc;
   if (batch == 0) return DPK_OK;
   if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0 || !desc->root_weight ||
-      (p.kind == DPK_LEAF_GAUSSIAN && !desc->leaf_p1))
+      false)
     return set_error(DPK_E_ARG, "null pointer argument");
   for (int e = 0; e < p.n_sum; ++e)
     if (!desc->sum_weight[e]) return set_error(DPK_E_ARG, "null sum_weight[%d]", e);
@@ -799,7 +831,7 @@ extern "C" int dpk_ratspn_leaf_forward(const dpk_ratspn_desc* desc, const float*
   int rc = make_plan(desc, batch, 0, &p);
   if (rc) return rc;
   if (batch == 0) return DPK_OK;
-  if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0 || (p.kind == DPK_LEAF_GAUSSIAN && !desc->leaf_p1))
+  if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0)
     return set_error(DPK_E_ARG, "null pointer argument");
   if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
   float* ws = static_cast<float*>(workspace);

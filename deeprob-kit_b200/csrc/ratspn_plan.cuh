@@ -1,12 +1,18 @@
 // ratspn_plan.cuh -- host-side launch plan / workspace layout of the RAT-SPN path.
 #pragma once
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dpk {
 
 // Workspace layout (all offsets in floats, each 256-byte aligned):
-//   leaf tables   tab   [G0][nKc][dim][ROWP]    row = {feature index (int bits), 0, 0, 0, NP*KC values}
-//                                              (Gaussian NP=2: 1/sigma[KC] | -mu/sigma[KC]; Bernoulli NP=1: logit[KC])
+//   leaf tables   tab   [G0][nKc][NCH][chunk]   chunk = {CHP header words | CH rows x NPK floats}; header word of
+//                                              row d = byte offset of feature f in the swizzled x tile
+//                                              (f*TB*4 + (f&31)*4; the reader XORs lane<<2 into it); row =
+//                                              Gaussian 1/sigma[KC] | -mu/sigma[KC], Bernoulli logit[KC]
 //                 cd    [G0][nKc][dim][KC]      per-dim additive constant (-log sigma - log sqrt(2pi) | -softplus)
 //                 cst   [G0][Kp]                sum over the real dims of cd
 //   sum level e   wsoft/wlog [P_e][nOc][Kin_e^2][OC]   softmax / log-softmax of the raw logits
@@ -15,11 +21,21 @@ namespace dpk {
 //   grad of act   gact[l] same shapes (only with DPK_F_SAVE_ACTIVATIONS)
 struct RatPlan {
   int kind, D, depth, R, K, O, C, dim, G0;
+  int fwd_kind;  // table/kernel flavour: DPK_LEAF_GAUSSIAN, DPK_LEAF_BERNOULLI or kLeafGaussUnit (scale == 1 everywhere)
   int n_sum;  // depth - 1 inner sum levels
   int64_t B, Bp;
   Chunking kc, oc, cc;
   int np;    // table values per channel on the fast path
-  int rowp;  // floats per table row: 4 (feature index + pad) + round_up(np * KC, 4)
+  // leaf kernel geometry (decided here because it fixes the table layout the prep kernel writes)
+  int leaf_mode;          // 2: 64-sample tile, 1: 32-sample tile, 0: wide fallback (no shared tile)
+  int leaf_tb;            // samples per tile
+  int leaf_npk;           // floats per table row = round_up(np * KC, 4)
+  int leaf_ch;            // table rows per ring chunk (<= 32)
+  int leaf_nch;           // chunks per (region, channel chunk) = ceil(dim / leaf_ch)
+  int leaf_chp;           // header words per chunk = round_up(leaf_ch, 4)
+  int leaf_chunk_floats;  // leaf_chp + leaf_ch * leaf_npk
+  int leaf_stages;        // ring depth (2..kLeafMaxStages)
+  size_t leaf_smem;       // dynamic shared memory of the leaf kernel
   int act_regions[DPK_MAX_LEVELS], act_ch[DPK_MAX_LEVELS];
   size_t off_tab, off_cd, off_cst;
   size_t off_wsoft[DPK_MAX_LEVELS], off_wlog[DPK_MAX_LEVELS], w_floats[DPK_MAX_LEVELS];
@@ -33,6 +49,63 @@ struct RatPlan {
 };
 
 static inline size_t align64(size_t v) { return (v + 63) / 64 * 64; }
+
+constexpr int kLeafMaxStages = 4;  // per-warp ring depth of TMA-bulk parameter chunks (upper bound)
+constexpr int kLeafWarps = 8;
+constexpr int kLeafGaussUnit = 2;  // internal leaf flavour: Gaussian with scale == 1 (desc->leaf_p1 == NULL)
+
+static inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// Shared memory of the leaf kernel = transposed x tile (D*TB floats) + one ring of kLeafStages chunks
+// per warp + mbarriers.  Picks the largest tile that leaves room for a useful ring, then the chunk
+// height that wastes the fewest padded rows.
+static inline void plan_leaf_geometry(RatPlan* p) {
+  const size_t smem_max = (size_t)max_dynamic_smem();
+  const int nsm = sm_count();
+  p->leaf_npk = (p->np * p->kc.chunk + 3) / 4 * 4;
+  const int want_stages = std::min(kLeafMaxStages, std::max(2, env_int("DPK_LEAF_STAGES", 2)));  // tuning knob
+  const int want_ch = env_int("DPK_LEAF_CH", 0);                                                  // tuning knob
+  auto fit = [&](int TB, int stages) -> int {  // best chunk height for this tile, 0 = does not fit
+    const size_t fixed = (size_t)p->D * TB * 4 + kLeafWarps * kLeafMaxStages * 8 + 128;
+    if (fixed >= smem_max) return 0;
+    const size_t per_stage = (smem_max - fixed) / ((size_t)kLeafWarps * stages * 4);  // floats
+    int chmax = 0;
+    for (int ch = 1; ch <= 32 && ch <= p->dim; ++ch)
+      if ((size_t)((ch + 3) / 4 * 4 + ch * p->leaf_npk) <= per_stage) chmax = ch;
+    if (chmax < 2 && chmax < p->dim) return 0;
+    if (want_ch > 0 && want_ch <= chmax) return want_ch;
+    // fewest chunks first (each chunk costs a barrier wait + a pipeline refill, measured ~450 cycles),
+    // then the fewest padded rows
+    const int nch = (int)ceil_div(p->dim, chmax);
+    int best = chmax;
+    for (int ch = chmax; ch >= 1 && ceil_div(p->dim, ch) == nch; --ch) best = ch;
+    return best;
+  };
+  // ring depth: 2 measured as good as 3/4 on B200 (the TMA latency hides behind one chunk of rows) and
+  // leaves room for taller chunks; fall back to shallower rings only when nothing else fits
+  auto choose = [&](int TB, int* stages) -> int {
+    for (int st = want_stages; st >= 2; --st) {
+      const int ch = fit(TB, st);
+      if (ch >= 8 || ch >= p->dim || (st == 2 && ch > 0)) { *stages = st; return ch; }
+    }
+    return 0;
+  };
+  int st64 = 0, st32 = 0;
+  const int ch64 = choose(64, &st64), ch32 = choose(32, &st32);
+  if (ch64 > 0 && ceil_div(p->B, 64) >= nsm) { p->leaf_mode = 2; p->leaf_tb = 64; p->leaf_ch = ch64; p->leaf_stages = st64; }
+  else if (ch32 > 0) { p->leaf_mode = 1; p->leaf_tb = 32; p->leaf_ch = ch32; p->leaf_stages = st32; }
+  else { p->leaf_mode = 0; p->leaf_tb = 32; p->leaf_ch = p->dim < 16 ? p->dim : 16; p->leaf_stages = 2; }
+  p->leaf_nch = (int)ceil_div(p->dim, p->leaf_ch);
+  p->leaf_chp = (p->leaf_ch + 3) / 4 * 4;
+  p->leaf_chunk_floats = p->leaf_chp + p->leaf_ch * p->leaf_npk;
+  p->leaf_smem = p->leaf_mode ? (size_t)p->D * p->leaf_tb * 4 +
+                                    (size_t)kLeafWarps * p->leaf_stages * p->leaf_chunk_floats * 4 +
+                                    kLeafWarps * kLeafMaxStages * 8
+                              : 0;
+}
 
 // returns 0 or a negative error (message set)
 static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t flags, RatPlan* p) {
@@ -50,11 +123,12 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
   p->n_sum = d->depth - 1;
   p->B = batch; p->Bp = round_up(batch > 0 ? batch : 1, 128);
   p->kc = pick_chunk(p->K); p->oc = pick_chunk(p->O); p->cc = pick_chunk(p->C);
-  p->np = (p->kind == DPK_LEAF_GAUSSIAN) ? 2 : 1;
+  p->fwd_kind = (p->kind == DPK_LEAF_GAUSSIAN && !d->leaf_p1) ? kLeafGaussUnit : p->kind;
+  p->np = (p->fwd_kind == DPK_LEAF_GAUSSIAN) ? 2 : 1;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = align64(off + n); return o; };
-  p->rowp = 4 + (p->np * p->kc.chunk + 3) / 4 * 4;
-  p->off_tab = take((size_t)p->G0 * p->kc.count * p->dim * p->rowp);
+  plan_leaf_geometry(p);
+  p->off_tab = take((size_t)p->G0 * p->kc.count * p->leaf_nch * p->leaf_chunk_floats);
   p->off_cd = take((size_t)p->G0 * p->kc.count * p->dim * p->kc.chunk);
   p->off_cst = take((size_t)p->G0 * p->kc.padded);
   for (int l = 0; l < p->depth; ++l) {

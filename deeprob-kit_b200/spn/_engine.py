@@ -30,6 +30,9 @@ class RatSpnCall:
     def __init__(self, base_layer, sum_weights: List[torch.Tensor], root_weight: Optional[torch.Tensor],
                  out_classes: int, sum_nodes: int, repetitions: int, device):
         p0, p1 = base_layer.leaf_parameters()
+        self.n_leaf = 1 if p1 is None else 2          # leaf tensors among the autograd inputs
+        if p1 is not None and getattr(base_layer, "unit_scale", lambda: False)():
+            p1 = None                                  # frozen scale == 1: NULL selects the unit-scale kernels
         self.keep = [_f32c(p0), _f32c(p1) if p1 is not None else None]
         self.sums = [_f32c(w) for w in sum_weights]
         self.root = _f32c(root_weight) if root_weight is not None else None
@@ -146,7 +149,7 @@ class _RatSpnLogProb(torch.autograd.Function):
         g = _lib.RatSpnGrads()
         gx = torch.zeros_like(x) if need[1] else None
         g.grad_x = gx.data_ptr() if gx is not None else None
-        n_leaf = 2 if call.keep[1] is not None else 1
+        n_leaf = call.n_leaf
         grads = []
         for i, shape in enumerate(ctx.param_shapes):
             grads.append(torch.zeros(shape, dtype=torch.float32, device=x.device) if need[2 + i] else None)

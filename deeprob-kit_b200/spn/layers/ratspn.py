@@ -126,6 +126,18 @@ class GaussianLayer(RegionGraphLayer):
     def leaf_parameters(self):
         return self.loc, self.scale
 
+    def unit_scale(self) -> bool:
+        """True when `scale` is frozen at 1 everywhere (the default, `optimize_scale=False`): the kernels
+        then take the cheaper t = x - mu path.  One device->host sync per parameter version, cached."""
+        s = self.scale
+        if s.requires_grad:
+            return False
+        key = (s._version, s.data_ptr(), str(s.device))
+        if getattr(self, "_unit_key", None) != key:
+            self._unit_val = bool((s == 1).all())
+            self._unit_key = key
+        return self._unit_val
+
     def distribution_mode(self) -> torch.Tensor:
         return self.loc
 

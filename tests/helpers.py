@@ -42,12 +42,12 @@ def oracle_state(orc, cfg, seed=0):
     return pg.ratspn_fill_state(state, cfg, seed)
 
 
-def product_model(cfg, device, seed=0):
+def product_model(cfg, device, seed=0, scale_grad=True):
     from deeprob_kit_b200.spn.models import BernoulliRatSpn, GaussianRatSpn
     cls = GaussianRatSpn if cfg["kind"] == "gaussian" else BernoulliRatSpn
     model = cls(**pg.ratspn_ctor_kwargs(cfg)).eval()
     state = pg.ratspn_fill_state(model.state_dict(), cfg, seed)
     model.load_state_dict(state)
-    if cfg["kind"] == "gaussian":
-        model.base_layer.scale.requires_grad_(True)
+    if cfg["kind"] == "gaussian" and scale_grad:
+        model.base_layer.scale.requires_grad_(True)     # also exercises d/dscale; disables the unit-scale kernels
     return model.to(device)

@@ -25,6 +25,19 @@ def test_log_prob_matches_oracle_and_golden(name):
     assert rel_err(out, load_golden("ratspn_" + name)["ll"]) < TOL
     # log_prob is the same call
     assert torch.equal(model.log_prob(x.to(DEV)).cpu(), out)
+    if cfg["kind"] == "gaussian" and not cfg.get("optimize_scale", False):
+        # frozen scale == 1 selects the unit-scale kernels: same values
+        unit = product_model(cfg, DEV, scale_grad=False)
+        assert unit.base_layer.unit_scale()
+        out_u = unit(x.to(DEV)).cpu()
+        assert rel_err(out_u, orc.log_prob(x)) < TOL
+        with torch.enable_grad():
+            xd = x.to(DEV).requires_grad_(True)
+            unit(xd).sum().backward()
+        ref = orc.grads(x, torch.ones_like(out), clean_nan=True)
+        tol = TOL + 4e-7 * float(out.abs().max())
+        assert norm_err(unit.base_layer.loc.grad, ref["loc"]) < 2 * tol
+        assert norm_err(torch.nan_to_num(xd.grad.cpu()), torch.nan_to_num(ref["x"])) < 2 * tol
 
 
 @pytest.mark.parametrize("name", sorted(pg.RATSPN_CASES))
