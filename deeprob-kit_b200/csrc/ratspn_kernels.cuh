@@ -1,0 +1,17 @@
+// ratspn_kernels.cuh -- host-side drivers shared by the RAT-SPN translation units.
+#pragma once
+#include "ratspn_plan.cuh"
+
+namespace dpk {
+
+int ratspn_check_ws(const RatPlan& p, const void* ws, size_t bytes);
+// leaf tables (tab / cd / cst) from the leaf parameters           [ratspn_leaf.cu]
+int ratspn_run_prep_leaf(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
+// softmax / log-softmax tables of every sum level and of the root [ratspn_einsum.cu]
+int ratspn_run_prep_weights(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
+// x -> act[0]                                                      [ratspn_leaf.cu]
+int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, float* ws, cudaStream_t st);
+// act[0] -> ... -> out (B, C)                                      [ratspn_einsum.cu]
+int ratspn_run_upper(const RatPlan& p, float* ws, float* out, cudaStream_t st);
+
+}  // namespace dpk

@@ -40,6 +40,7 @@ struct RatPlan {
   size_t off_tab, off_cd, off_cst;
   size_t off_wsoft[DPK_MAX_LEVELS], off_wlog[DPK_MAX_LEVELS], w_floats[DPK_MAX_LEVELS];
   size_t off_rsoft, off_rlog, r_floats;
+  size_t off_rtmp;  // [R][C][Bp] per-partition partials of the root
   size_t off_act[DPK_MAX_LEVELS], off_gact[DPK_MAX_LEVELS];
   // backward scratch (only with DPK_F_SAVE_ACTIVATIONS): posterior-count accumulators in the chunked
   // weight layouts and leaf moment accumulators in the parameter layout (G0,K,dim)
@@ -147,6 +148,7 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     p->off_rsoft = take(p->r_floats);
     p->off_rlog = take(p->r_floats);
   }
+  p->off_rtmp = take((size_t)p->R * p->C * p->Bp);
   for (int l = 0; l < p->depth; ++l)
     p->off_act[l] = take((size_t)p->act_regions[l] * p->act_ch[l] * p->Bp);
   for (int l = 0; l < p->depth; ++l)
