@@ -105,6 +105,12 @@ class RatSpnEmStats(ctypes.Structure):
     ]
 
 
+class DgcProductDesc(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ("channels", "height", "width", "out_channels", "out_height", "out_width",
+                                     "pad_top", "pad_left", "stride_h", "stride_w", "dilation_h", "dilation_w",
+                                     "depthwise")]
+
+
 # name -> (restype, argtypes); every symbol include/deeprob_b200.h declares must be listed here
 # (tests/test_cabi.py cross-checks this table against the header and the built library).
 SIGNATURES = {
@@ -121,6 +127,14 @@ SIGNATURES = {
     "dpk_ratspn_leaf_forward": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dpk_outer_sum_forward": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "dpk_mixture_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dpk_dgc_leaf_forward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "dpk_dgc_leaf_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dpk_dgc_product_forward": (ctypes.c_int, [ctypes.POINTER(DgcProductDesc), c_vp, c_i64, c_vp, c_vp]),
+    "dpk_dgc_product_backward": (ctypes.c_int, [ctypes.POINTER(DgcProductDesc), c_vp, c_i64, c_vp, c_vp]),
+    "dpk_dgc_sum_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dpk_dgc_sum_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dpk_dgc_root_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "dpk_dgc_root_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 
 

@@ -1,0 +1,616 @@
+// dgcspn.cu -- DGC-SPN layers (NCHW fp32, the reference's tensor layout) with their backward passes.
+//
+// Reference (deeprob-kit, paths relative to /root/reference):
+//   SpatialGaussianLayer.forward  deeprob/spn/layers/dgcspn.py:101-120  per-pixel Normal LL, NaN -> 0, sum over C_in
+//   SpatialProductLayer.forward   deeprob/spn/layers/dgcspn.py:224-236  zero pad + 2x2 dilated conv with 0/1 weights
+//   SpatialSumLayer.forward       deeprob/spn/layers/dgcspn.py:289-304  logsumexp_i(x + log_softmax_i W) per pixel
+//   SpatialRootLayer.forward      deeprob/spn/layers/dgcspn.py:343-355  flatten + weighted logsumexp
+// The reference materialises (B,C_out,C_in,H,W) in the sum layer and runs the product as a real
+// convolution multiplying by 1.0; here the product is a 4-tap gather-add and the sum layer is a
+// per-pixel mixture in the linear domain (one exp per input, max-shifted, exact log-domain fallback).
+// Lanes run along the contiguous H*W axis, so every access of x / W / out is coalesced, and the
+// per-pixel mixture weights are read once per CTA and reused over a slice of the batch.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dpk {
+
+// =================================================================================================
+// Leaf
+// =================================================================================================
+__global__ void dgc_leaf_fwd_kernel(const float* __restrict__ x, const float* __restrict__ loc,
+                                    const float* __restrict__ scale, float* __restrict__ out, int64_t B, int Cin, int K,
+                                    int HW) {
+  const int64_t total = B * K * HW;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(idx % HW);
+    const int k = (int)((idx / HW) % K);
+    const int64_t b = idx / ((int64_t)HW * K);
+    float acc = 0.f;
+    for (int c = 0; c < Cin; ++c) {
+      const float xv = x[(b * Cin + c) * HW + hw];
+      const size_t pi = ((size_t)k * Cin + c) * HW + hw;
+      const float sg = __ldg(scale + pi), mu = __ldg(loc + pi);
+      const float t = (xv - mu) / sg;
+      acc += nan_to_num(-0.5f * t * t - logf(sg) - kLogSqrt2Pi);
+    }
+    out[idx] = acc;
+  }
+}
+
+// gx[b,c,hw] = sum_k g * -(x-mu)/s^2   (zero where x is non-finite: nan_to_num'ed terms have no gradient)
+__global__ void dgc_leaf_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ loc,
+                                      const float* __restrict__ scale, const float* __restrict__ g,
+                                      float* __restrict__ gx, int64_t B, int Cin, int K, int HW) {
+  const int64_t total = B * Cin * HW;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(idx % HW);
+    const int c = (int)((idx / HW) % Cin);
+    const int64_t b = idx / ((int64_t)HW * Cin);
+    const float xv = x[idx];
+    float acc = 0.f;
+    if (fabsf(xv) <= FLT_MAX) {
+      for (int k = 0; k < K; ++k) {
+        const size_t pi = ((size_t)k * Cin + c) * HW + hw;
+        const float sg = __ldg(scale + pi), mu = __ldg(loc + pi);
+        acc -= g[(b * K + k) * HW + hw] * (xv - mu) / (sg * sg);
+      }
+    }
+    gx[idx] = acc;
+  }
+}
+
+// thread = parameter element (k,c,hw); batch split over blockIdx.y, partial sums merged with atomics
+__global__ void dgc_leaf_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ loc,
+                                          const float* __restrict__ scale, const float* __restrict__ g,
+                                          float* __restrict__ gloc, float* __restrict__ gscale, int64_t B, int Cin, int K,
+                                          int HW, int64_t per_slice) {
+  const int64_t n = (int64_t)K * Cin * HW;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int hw = (int)(idx % HW);
+  const int c = (int)((idx / HW) % Cin);
+  const int k = (int)(idx / ((int64_t)HW * Cin));
+  const float mu = loc[idx], sg = scale[idx];
+  const float inv = 1.0f / sg, inv2 = inv * inv;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  float s_mu = 0.f, s_sg = 0.f;
+  for (int64_t b = b0; b < b1; ++b) {
+    const float xv = x[(b * Cin + c) * HW + hw];
+    if (!(fabsf(xv) <= FLT_MAX)) continue;
+    const float gv = g[(b * K + k) * HW + hw];
+    const float d = xv - mu;
+    s_mu = fmaf(gv, d * inv2, s_mu);
+    s_sg = fmaf(gv, d * d * inv2 * inv - inv, s_sg);
+  }
+  if (gloc && s_mu != 0.f) atomicAdd(gloc + idx, s_mu);
+  if (gscale && s_sg != 0.f) atomicAdd(gscale + idx, s_sg);
+}
+
+// =================================================================================================
+// Product (2x2 taps, dilation, stride, zero padding = log 1)
+// =================================================================================================
+struct ProdDesc {
+  int C, H, W, OC, OH, OW, pad_top, pad_left, sh, sw, dh, dw, depthwise;
+};
+
+__device__ __forceinline__ int prod_in_channel(const ProdDesc& d, int oc, int tap) {
+  if (d.depthwise) return oc;
+  // itertools.product(range(C), repeat=4): tap 0 (kh=0,kw=0) is the most significant digit
+  int div = 1;
+  for (int t = 3; t > tap; --t) div *= d.C;
+  return (oc / div) % d.C;
+}
+
+__global__ void dgc_product_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t B, ProdDesc d) {
+  const int64_t total = B * d.OC * d.OH * d.OW;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(idx % d.OW);
+    const int oh = (int)((idx / d.OW) % d.OH);
+    const int oc = (int)((idx / ((int64_t)d.OW * d.OH)) % d.OC);
+    const int64_t b = idx / ((int64_t)d.OW * d.OH * d.OC);
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top;
+      const int xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
+      if (y >= 0 && y < d.H && xx >= 0 && xx < d.W)
+        acc += x[((b * d.C + prod_in_channel(d, oc, tap)) * d.H + y) * d.W + xx];
+    }
+    out[idx] = acc;
+  }
+}
+
+// depthwise: gather form (thread = input element); otherwise scatter with atomics (thread = output element)
+__global__ void dgc_product_bwd_depthwise_kernel(const float* __restrict__ g, float* __restrict__ gx, int64_t B, ProdDesc d) {
+  const int64_t total = B * d.C * d.H * d.W;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(idx % d.W);
+    const int y = (int)((idx / d.W) % d.H);
+    const int64_t bc = idx / ((int64_t)d.W * d.H);
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int ny = y + d.pad_top - (tap >> 1) * d.dh, nx = xx + d.pad_left - (tap & 1) * d.dw;
+      if (ny < 0 || nx < 0 || ny % d.sh || nx % d.sw) continue;
+      const int oh = ny / d.sh, ow = nx / d.sw;
+      if (oh < d.OH && ow < d.OW) acc += g[(bc * d.OH + oh) * d.OW + ow];
+    }
+    gx[idx] = acc;
+  }
+}
+
+__global__ void dgc_product_bwd_scatter_kernel(const float* __restrict__ g, float* __restrict__ gx, int64_t B, ProdDesc d) {
+  const int64_t total = B * d.OC * d.OH * d.OW;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const float gv = g[idx];
+    if (gv == 0.f) continue;
+    const int ow = (int)(idx % d.OW);
+    const int oh = (int)((idx / d.OW) % d.OH);
+    const int oc = (int)((idx / ((int64_t)d.OW * d.OH)) % d.OC);
+    const int64_t b = idx / ((int64_t)d.OW * d.OH * d.OC);
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top;
+      const int xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
+      if (y >= 0 && y < d.H && xx >= 0 && xx < d.W)
+        atomicAdd(gx + ((b * d.C + prod_in_channel(d, oc, tap)) * d.H + y) * d.W + xx, gv);
+    }
+  }
+}
+
+// =================================================================================================
+// Per-pixel mixture (SpatialSumLayer)
+// =================================================================================================
+// softmax / log-softmax over the input-channel axis of weight (O, I, HW); thread = (o, hw)
+__global__ void dgc_sum_prep_kernel(const float* __restrict__ w, float* __restrict__ wsoft, float* __restrict__ wlog,
+                                    int O, int I, int HW) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= O * HW) return;
+  const int hw = idx % HW, o = idx / HW;
+  const float* base = w + (size_t)o * I * HW + hw;
+  float m = -INFINITY;
+  for (int i = 0; i < I; ++i) m = fmaxf(m, base[(size_t)i * HW]);
+  float s = 0.f;
+  for (int i = 0; i < I; ++i) s += expf(base[(size_t)i * HW] - m);
+  const float lse = m + logf(s);
+  for (int i = 0; i < I; ++i) {
+    const float lw = base[(size_t)i * HW] - lse;
+    wlog[(size_t)o * I * HW + (size_t)i * HW + hw] = lw;
+    wsoft[(size_t)o * I * HW + (size_t)i * HW + hw] = expf(lw);
+  }
+}
+
+constexpr int kSumNB = 4;  // samples a thread carries at once (weight loads amortised over them)
+
+// thread = pixel; CTA.y = batch slice; loops over output chunks of OC and over the slice in groups of NB
+template <int OC>
+__global__ void __launch_bounds__(128) dgc_sum_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wsoft,
+                                                          const float* __restrict__ wlog, float* __restrict__ out,
+                                                          int64_t B, int I, int O, int HW, int64_t per_slice) {
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hw >= HW) return;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  for (int o0 = 0; o0 < O; o0 += OC) {
+    for (int64_t bb = b0; bb < b1; bb += kSumNB) {
+      float m[kSumNB], acc[kSumNB][OC];
+#pragma unroll
+      for (int s = 0; s < kSumNB; ++s) {
+        m[s] = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) acc[s][o] = 0.f;
+      }
+      for (int i = 0; i < I; ++i) {
+        float w[OC];
+#pragma unroll
+        for (int o = 0; o < OC; ++o) w[o] = (o0 + o < O) ? __ldg(wsoft + ((size_t)(o0 + o) * I + i) * HW + hw) : 0.f;
+#pragma unroll
+        for (int s = 0; s < kSumNB; ++s) {
+          if (bb + s >= b1) continue;
+          const float xv = x[((bb + s) * I + i) * HW + hw];
+          if (xv > m[s]) {                       // online max: rescale what has been accumulated so far
+            const float sc = __expf(m[s] - xv);  // m = -inf -> 0
+#pragma unroll
+            for (int o = 0; o < OC; ++o) acc[s][o] *= sc;
+            m[s] = xv;
+          }
+          const float e = (m[s] == -INFINITY) ? 0.f : __expf(xv - m[s]);
+#pragma unroll
+          for (int o = 0; o < OC; ++o) acc[s][o] = fmaf(w[o], e, acc[s][o]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < kSumNB; ++s) {
+        if (bb + s >= b1) continue;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+          if (o0 + o >= O) continue;
+          float y;
+          if (acc[s][o] >= 1e-18f && acc[s][o] <= FLT_MAX && fabsf(m[s]) <= FLT_MAX) {
+            y = m[s] + __logf(acc[s][o]);
+          } else {  // exact log-domain evaluation
+            float mm = -INFINITY;
+            for (int i = 0; i < I; ++i)
+              mm = fmaxf(mm, x[((bb + s) * I + i) * HW + hw] + wlog[((size_t)(o0 + o) * I + i) * HW + hw]);
+            if (!(fabsf(mm) <= FLT_MAX)) {
+              y = mm;
+            } else {
+              float ss = 0.f;
+              for (int i = 0; i < I; ++i)
+                ss += expf(x[((bb + s) * I + i) * HW + hw] + wlog[((size_t)(o0 + o) * I + i) * HW + hw] - mm);
+              y = mm + logf(ss);
+            }
+          }
+          out[((bb + s) * O + o0 + o) * HW + hw] = y;
+        }
+      }
+    }
+  }
+}
+
+// Backward: posterior of input i under output o is w[o,i]*exp(x_i - y_o).
+//   gx[b,i]    = sum_o g[b,o] * w[o,i] * exp(x_i - y_o)
+//   N[o,i,hw] += sum_b g[b,o] * w[o,i] * exp(x_i - y_o)       (then grad_raw = N - softmax * sum_i N)
+// thread = pixel, CTA.y = batch slice; the N accumulators of an (OC x IC) block stay in registers over
+// the slice and are merged with atomics.
+template <int OC, int IC>
+__global__ void __launch_bounds__(128) dgc_sum_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wsoft,
+                                                          const float* __restrict__ y, const float* __restrict__ g,
+                                                          float* __restrict__ gx, float* __restrict__ nstat, int64_t B,
+                                                          int I, int O, int HW, int64_t per_slice) {
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hw >= HW) return;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  for (int i0 = 0; i0 < I; i0 += IC) {
+    for (int o0 = 0; o0 < O; o0 += OC) {
+      float w[OC][IC], n[OC][IC];
+#pragma unroll
+      for (int o = 0; o < OC; ++o)
+#pragma unroll
+        for (int i = 0; i < IC; ++i) {
+          w[o][i] = (o0 + o < O && i0 + i < I) ? __ldg(wsoft + ((size_t)(o0 + o) * I + i0 + i) * HW + hw) : 0.f;
+          n[o][i] = 0.f;
+        }
+      for (int64_t b = b0; b < b1; ++b) {
+        float xv[IC], gi[IC];
+#pragma unroll
+        for (int i = 0; i < IC; ++i) { xv[i] = (i0 + i < I) ? x[(b * I + i0 + i) * HW + hw] : -INFINITY; gi[i] = 0.f; }
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+          if (o0 + o >= O) continue;
+          const float gv = g[(b * O + o0 + o) * HW + hw];
+          const float yv = y[(b * O + o0 + o) * HW + hw];
+          if (gv == 0.f || !(fabsf(yv) <= FLT_MAX)) continue;
+#pragma unroll
+          for (int i = 0; i < IC; ++i) {
+            const float post = gv * w[o][i] * __expf(fminf(xv[i] - yv, 80.f));
+            n[o][i] += post;
+            gi[i] += post;
+          }
+        }
+        if (gx) {
+#pragma unroll
+          for (int i = 0; i < IC; ++i)
+            if (i0 + i < I) {
+              float* dst = gx + (b * I + i0 + i) * HW + hw;
+              *dst = (o0 == 0) ? gi[i] : *dst + gi[i];   // output chunks accumulate in order within the thread
+            }
+        }
+      }
+      if (nstat) {
+#pragma unroll
+        for (int o = 0; o < OC; ++o)
+#pragma unroll
+          for (int i = 0; i < IC; ++i)
+            if (o0 + o < O && i0 + i < I && n[o][i] != 0.f)
+              atomicAdd(nstat + ((size_t)(o0 + o) * I + i0 + i) * HW + hw, n[o][i]);
+      }
+    }
+  }
+}
+
+// grad_raw[o,i,hw] += N - softmax * sum_i N
+__global__ void dgc_sum_finalize_kernel(const float* __restrict__ wsoft, const float* __restrict__ nstat,
+                                        float* __restrict__ gw, int O, int I, int HW) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= O * HW) return;
+  const int hw = idx % HW, o = idx / HW;
+  const size_t base = (size_t)o * I * HW + hw;
+  float tot = 0.f;
+  for (int i = 0; i < I; ++i) tot += nstat[base + (size_t)i * HW];
+  for (int i = 0; i < I; ++i) gw[base + (size_t)i * HW] += nstat[base + (size_t)i * HW] - wsoft[base + (size_t)i * HW] * tot;
+}
+
+// =================================================================================================
+// Root: out[b,c] = logsumexp_q(x[b,q] + log_softmax_q W[c,q]);  one CTA per sample
+// =================================================================================================
+__global__ void dgc_root_prep_kernel(const float* __restrict__ w, float* __restrict__ wlog, int C, int64_t Q) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float* row = w + (size_t)c * Q;
+  float m = -INFINITY;
+  for (int64_t q = threadIdx.x; q < Q; q += blockDim.x) m = fmaxf(m, row[q]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int64_t q = threadIdx.x; q < Q; q += blockDim.x) s += expf(row[q] - m);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) s += red[i];
+  const float lse = m + logf(s);
+  for (int64_t q = threadIdx.x; q < Q; q += blockDim.x) wlog[(size_t)c * Q + q] = row[q] - lse;
+}
+
+__global__ void __launch_bounds__(256) dgc_root_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wlog,
+                                                           float* __restrict__ out, int64_t Q, int C) {
+  __shared__ float red[8];
+  const int64_t b = blockIdx.x;
+  const float* row = x + b * Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = 0; c < C; ++c) {
+    const float* wl = wlog + (size_t)c * Q;
+    float m = -INFINITY;
+    for (int64_t q = threadIdx.x; q < Q; q += 256) m = fmaxf(m, row[q] + __ldg(wl + q));
+    m = warp_max(m);
+    __syncthreads();
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    float y = m;
+    if (fabsf(m) <= FLT_MAX) {
+      float s = 0.f;
+      for (int64_t q = threadIdx.x; q < Q; q += 256) s += __expf(row[q] + __ldg(wl + q) - m);
+      s = warp_sum(s);
+      __syncthreads();
+      if (lane == 0) red[warp] = s;
+      __syncthreads();
+      s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i];
+      y = m + logf(s);
+    }
+    if (threadIdx.x == 0) out[b * C + c] = y;
+  }
+}
+
+// gx[b,q] = sum_c g[b,c] * exp(x_q + lw_cq - out_bc);  N[c,q] += g[b,c] * exp(...)   (thread = q, batch slice = CTA.y)
+__global__ void dgc_root_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wlog,
+                                    const float* __restrict__ out, const float* __restrict__ g, float* __restrict__ gx,
+                                    float* __restrict__ nstat, int64_t B, int64_t Q, int C, int64_t per_slice) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  for (int c = 0; c < C; ++c) {
+    const float lw = wlog[(size_t)c * Q + q];
+    float n = 0.f;
+    for (int64_t b = b0; b < b1; ++b) {
+      const float gv = g[b * C + c], ov = out[b * C + c];
+      float post = 0.f;
+      if (gv != 0.f && fabsf(ov) <= FLT_MAX) post = gv * __expf(fminf(x[b * Q + q] + lw - ov, 80.f));
+      n += post;
+      if (gx) {
+        float* dst = gx + b * Q + q;
+        *dst = (c == 0) ? post : *dst + post;
+      }
+    }
+    if (nstat && n != 0.f) atomicAdd(nstat + (size_t)c * Q + q, n);
+  }
+}
+
+// grad_raw[c,q] += N[c,q] - softmax[c,q] * sum_q N[c,q]
+__global__ void dgc_root_finalize_kernel(const float* __restrict__ wlog, const float* __restrict__ nstat,
+                                         float* __restrict__ gw, int64_t Q) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  for (int64_t q = threadIdx.x; q < Q; q += blockDim.x) s += nstat[(size_t)c * Q + q];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) s += red[i];
+  for (int64_t q = threadIdx.x; q < Q; q += blockDim.x)
+    gw[(size_t)c * Q + q] += nstat[(size_t)c * Q + q] - expf(wlog[(size_t)c * Q + q]) * s;
+}
+
+static int grid_for(int64_t total, int threads) {
+  return (int)std::min<int64_t>(ceil_div(total, threads), (int64_t)sm_count() * 32);
+}
+
+// batch slices so that (pixel blocks x slices) fills the machine about 4x
+static int64_t slice_len(int64_t B, int64_t blocks_x, int min_len) {
+  int64_t slices = std::max<int64_t>(1, ceil_div((int64_t)4 * sm_count(), blocks_x));
+  slices = std::min<int64_t>(slices, std::max<int64_t>(1, B / min_len));
+  return round_up(ceil_div(B, slices), kSumNB);
+}
+
+static ProdDesc to_prod(const dpk_dgc_product_desc* d) {
+  ProdDesc p;
+  p.C = d->channels; p.H = d->height; p.W = d->width; p.OC = d->out_channels; p.OH = d->out_height; p.OW = d->out_width;
+  p.pad_top = d->pad_top; p.pad_left = d->pad_left; p.sh = d->stride_h; p.sw = d->stride_w; p.dh = d->dilation_h;
+  p.dw = d->dilation_w; p.depthwise = d->depthwise;
+  return p;
+}
+
+}  // namespace dpk
+
+using namespace dpk;
+
+extern "C" int dpk_dgc_leaf_forward(const float* x, const float* loc, const float* scale, int64_t batch,
+                                    int32_t in_channels, int32_t out_channels, int32_t hw, float* out, void* stream) {
+  if (batch < 0 || in_channels <= 0 || out_channels <= 0 || hw <= 0) return set_error(DPK_E_ARG, "dgc_leaf: bad sizes");
+  if (batch == 0) return DPK_OK;
+  if (!x || !loc || !scale || !out) return set_error(DPK_E_ARG, "dgc_leaf: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CAT_DGC, st);
+  dgc_leaf_fwd_kernel<<<grid_for(batch * out_channels * hw, 256), 256, 0, st>>>(x, loc, scale, out, batch, in_channels,
+                                                                                 out_channels, hw);
+  DPK_LAUNCH_CHECK("dgc_leaf_fwd_kernel");
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_leaf_backward(const float* x, const float* loc, const float* scale, const float* grad_out,
+                                     int64_t batch, int32_t in_channels, int32_t out_channels, int32_t hw, float* grad_x,
+                                     float* grad_loc, float* grad_scale, void* stream) {
+  if (batch < 0 || in_channels <= 0 || out_channels <= 0 || hw <= 0) return set_error(DPK_E_ARG, "dgc_leaf_bwd: bad sizes");
+  if (batch == 0) return DPK_OK;
+  if (!x || !loc || !scale || !grad_out) return set_error(DPK_E_ARG, "dgc_leaf_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (grad_x) {
+    ProfScope prof(CAT_DGC_BWD, st);
+    dgc_leaf_bwd_x_kernel<<<grid_for(batch * in_channels * hw, 256), 256, 0, st>>>(x, loc, scale, grad_out, grad_x, batch,
+                                                                                    in_channels, out_channels, hw);
+    DPK_LAUNCH_CHECK("dgc_leaf_bwd_x_kernel");
+  }
+  if (grad_loc || grad_scale) {
+    const int64_t n = (int64_t)out_channels * in_channels * hw;
+    const int64_t bx = ceil_div(n, 128);
+    const int64_t per = slice_len(batch, bx, 32);
+    ProfScope prof(CAT_DGC_BWD, st);
+    dgc_leaf_bwd_param_kernel<<<dim3((unsigned)bx, (unsigned)ceil_div(batch, per)), 128, 0, st>>>(
+        x, loc, scale, grad_out, grad_loc, grad_scale, batch, in_channels, out_channels, hw, per);
+    DPK_LAUNCH_CHECK("dgc_leaf_bwd_param_kernel");
+  }
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_product_forward(const dpk_dgc_product_desc* desc, const float* x, int64_t batch, float* out,
+                                       void* stream) {
+  if (!desc || batch < 0) return set_error(DPK_E_ARG, "dgc_product: bad arguments");
+  if (batch == 0) return DPK_OK;
+  if (!x || !out) return set_error(DPK_E_ARG, "dgc_product: null pointer");
+  const ProdDesc d = to_prod(desc);
+  if (d.C <= 0 || d.OC <= 0 || d.OH <= 0 || d.OW <= 0 || d.sh <= 0 || d.sw <= 0)
+    return set_error(DPK_E_ARG, "dgc_product: bad descriptor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CAT_DGC, st);
+  dgc_product_fwd_kernel<<<grid_for(batch * d.OC * d.OH * d.OW, 256), 256, 0, st>>>(x, out, batch, d);
+  DPK_LAUNCH_CHECK("dgc_product_fwd_kernel");
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_product_backward(const dpk_dgc_product_desc* desc, const float* grad_out, int64_t batch,
+                                        float* grad_x, void* stream) {
+  if (!desc || batch < 0) return set_error(DPK_E_ARG, "dgc_product_bwd: bad arguments");
+  if (batch == 0) return DPK_OK;
+  if (!grad_out || !grad_x) return set_error(DPK_E_ARG, "dgc_product_bwd: null pointer");
+  const ProdDesc d = to_prod(desc);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CAT_DGC_BWD, st, d.depthwise ? 1 : 2);
+  if (d.depthwise) {
+    dgc_product_bwd_depthwise_kernel<<<grid_for(batch * d.C * d.H * d.W, 256), 256, 0, st>>>(grad_out, grad_x, batch, d);
+  } else {
+    DPK_CUDA_TRY(cudaMemsetAsync(grad_x, 0, (size_t)batch * d.C * d.H * d.W * sizeof(float), st));
+    dgc_product_bwd_scatter_kernel<<<grid_for(batch * d.OC * d.OH * d.OW, 256), 256, 0, st>>>(grad_out, grad_x, batch, d);
+  }
+  DPK_LAUNCH_CHECK("dgc_product_bwd_kernel");
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_sum_forward(const float* x, const float* weight, int64_t batch, int32_t in_channels,
+                                   int32_t out_channels, int32_t hw, float* out, float* scratch, void* stream) {
+  if (batch < 0 || in_channels <= 0 || out_channels <= 0 || hw <= 0) return set_error(DPK_E_ARG, "dgc_sum: bad sizes");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !out || !scratch) return set_error(DPK_E_ARG, "dgc_sum: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nw = (size_t)out_channels * in_channels * hw;
+  float* wsoft = scratch;
+  float* wlog = scratch + nw;
+  ProfScope prof(CAT_DGC, st, 2);
+  dgc_sum_prep_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(weight, wsoft, wlog, out_channels, in_channels, hw);
+  DPK_LAUNCH_CHECK("dgc_sum_prep_kernel");
+  const int64_t bx = ceil_div(hw, 128);
+  const int64_t per = slice_len(batch, bx, 4 * kSumNB);
+  dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
+  const Chunking oc = pick_chunk(out_channels);
+  switch (oc.chunk > 8 ? 8 : oc.chunk) {   // OC = 8 covers 10/16 in two passes without blowing up registers
+    case 2: dgc_sum_fwd_kernel<2><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
+    case 4: dgc_sum_fwd_kernel<4><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
+    default: dgc_sum_fwd_kernel<8><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
+  }
+  DPK_LAUNCH_CHECK("dgc_sum_fwd_kernel");
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_sum_backward(const float* x, const float* weight, const float* out, const float* grad_out,
+                                    int64_t batch, int32_t in_channels, int32_t out_channels, int32_t hw, float* grad_x,
+                                    float* grad_weight, float* scratch, void* stream) {
+  if (batch < 0 || in_channels <= 0 || out_channels <= 0 || hw <= 0) return set_error(DPK_E_ARG, "dgc_sum_bwd: bad sizes");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !out || !grad_out || !scratch) return set_error(DPK_E_ARG, "dgc_sum_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nw = (size_t)out_channels * in_channels * hw;
+  float* wsoft = scratch;
+  float* wlog = scratch + nw;
+  float* nstat = scratch + 2 * nw;
+  ProfScope prof(CAT_DGC_BWD, st, grad_weight ? 3 : 2);
+  dgc_sum_prep_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(weight, wsoft, wlog, out_channels, in_channels, hw);
+  DPK_LAUNCH_CHECK("dgc_sum_prep_kernel");
+  if (grad_weight) DPK_CUDA_TRY(cudaMemsetAsync(nstat, 0, nw * sizeof(float), st));
+  const int64_t bx = ceil_div(hw, 128);
+  const int64_t per = slice_len(batch, bx, 16);
+  dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
+  float* ns = grad_weight ? nstat : nullptr;
+  if (out_channels <= 4 && in_channels <= 4)
+    dgc_sum_bwd_kernel<4, 4><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per);
+  else if (out_channels <= 4)
+    dgc_sum_bwd_kernel<4, 8><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per);
+  else
+    dgc_sum_bwd_kernel<8, 8><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per);
+  DPK_LAUNCH_CHECK("dgc_sum_bwd_kernel");
+  if (grad_weight) {
+    dgc_sum_finalize_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(wsoft, nstat, grad_weight, out_channels,
+                                                                              in_channels, hw);
+    DPK_LAUNCH_CHECK("dgc_sum_finalize_kernel");
+  }
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_root_forward(const float* x, const float* weight, int64_t batch, int64_t features,
+                                    int32_t out_classes, float* out, float* scratch, void* stream) {
+  if (batch < 0 || features <= 0 || out_classes <= 0) return set_error(DPK_E_ARG, "dgc_root: bad sizes");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !out || !scratch) return set_error(DPK_E_ARG, "dgc_root: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CAT_DGC, st, 2);
+  dgc_root_prep_kernel<<<out_classes, 256, 0, st>>>(weight, scratch, out_classes, features);
+  DPK_LAUNCH_CHECK("dgc_root_prep_kernel");
+  dgc_root_fwd_kernel<<<(unsigned)batch, 256, 0, st>>>(x, scratch, out, features, out_classes);
+  DPK_LAUNCH_CHECK("dgc_root_fwd_kernel");
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_root_backward(const float* x, const float* weight, const float* out, const float* grad_out,
+                                     int64_t batch, int64_t features, int32_t out_classes, float* grad_x,
+                                     float* grad_weight, float* scratch, void* stream) {
+  if (batch < 0 || features <= 0 || out_classes <= 0) return set_error(DPK_E_ARG, "dgc_root_bwd: bad sizes");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !out || !grad_out || !scratch) return set_error(DPK_E_ARG, "dgc_root_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nw = (size_t)out_classes * features;
+  float* wlog = scratch;
+  float* nstat = scratch + nw;
+  ProfScope prof(CAT_DGC_BWD, st, grad_weight ? 3 : 2);
+  dgc_root_prep_kernel<<<out_classes, 256, 0, st>>>(weight, wlog, out_classes, features);
+  DPK_LAUNCH_CHECK("dgc_root_prep_kernel");
+  if (grad_weight) DPK_CUDA_TRY(cudaMemsetAsync(nstat, 0, nw * sizeof(float), st));
+  const int64_t bx = ceil_div(features, 128);
+  const int64_t per = slice_len(batch, bx, 16);
+  dgc_root_bwd_kernel<<<dim3((unsigned)bx, (unsigned)ceil_div(batch, per)), 128, 0, st>>>(
+      x, wlog, out, grad_out, grad_x, grad_weight ? nstat : nullptr, batch, features, out_classes, per);
+  DPK_LAUNCH_CHECK("dgc_root_bwd_kernel");
+  if (grad_weight) {
+    dgc_root_finalize_kernel<<<out_classes, 256, 0, st>>>(wlog, nstat, grad_weight, features);
+    DPK_LAUNCH_CHECK("dgc_root_finalize_kernel");
+  }
+  return DPK_OK;
+}

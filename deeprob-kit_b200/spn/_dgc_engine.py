@@ -1,0 +1,154 @@
+"""ctypes glue + autograd Functions of the DGC-SPN layers (csrc/dgcspn.cu).  Each layer is one
+autograd node (the reference's `mpe` differentiates w.r.t. the base layer output, so the layers have
+to stay separately differentiable: deeprob/spn/models/dgcspn.py:153-184)."""
+import ctypes
+
+import torch
+
+from .. import _lib
+from ._engine import _PTR, _f32c, _ptr
+
+
+def _stream(dev):
+    return _PTR(_lib.stream_ptr(dev))
+
+
+def _check4d(x, what):
+    _lib.require_cuda(x, what)
+    if x.dim() != 4:
+        raise ValueError("%s: expected a (B, C, H, W) tensor, got %s" % (what, tuple(x.shape)))
+    return _f32c(x)
+
+
+class _Leaf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, loc, scale):
+        x, loc, scale = _f32c(x), _f32c(loc), _f32c(scale)
+        b, cin, h, w = x.shape
+        k = loc.shape[0]
+        out = torch.empty(b, k, h, w, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_dgc_leaf_forward(_ptr(x), _ptr(loc), _ptr(scale), b, cin, k, h * w, _ptr(out), _stream(x.device))
+        _lib.check(rc, "dpk_dgc_leaf_forward")
+        ctx.save_for_backward(x, loc, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, loc, scale = ctx.saved_tensors
+        g = _f32c(g)
+        b, cin, h, w = x.shape
+        k = loc.shape[0]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gl = torch.zeros_like(loc) if ctx.needs_input_grad[1] else None
+        gs = torch.zeros_like(scale) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_dgc_leaf_backward(_ptr(x), _ptr(loc), _ptr(scale), _ptr(g), b, cin, k, h * w, _ptr(gx),
+                                                  _ptr(gl), _ptr(gs), _stream(x.device))
+        _lib.check(rc, "dpk_dgc_leaf_backward")
+        return gx, gl, gs
+
+
+class _Product(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, desc):
+        x = _f32c(x)
+        b = x.shape[0]
+        out = torch.empty(b, desc.out_channels, desc.out_height, desc.out_width, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_dgc_product_forward(ctypes.byref(desc), _ptr(x), b, _ptr(out), _stream(x.device))
+        _lib.check(rc, "dpk_dgc_product_forward")
+        ctx.desc, ctx.in_shape = desc, x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        gx = torch.empty(ctx.in_shape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            rc = _lib.lib().dpk_dgc_product_backward(ctypes.byref(ctx.desc), _ptr(g), g.shape[0], _ptr(gx), _stream(g.device))
+        _lib.check(rc, "dpk_dgc_product_backward")
+        return gx, None
+
+
+class _Sum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x, weight = _f32c(x), _f32c(weight)
+        b, cin, h, w = x.shape
+        cout = weight.shape[0]
+        out = torch.empty(b, cout, h, w, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(2 * weight.numel(), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_dgc_sum_forward(_ptr(x), _ptr(weight), b, cin, cout, h * w, _ptr(out), _ptr(scratch),
+                                                _stream(x.device))
+        _lib.check(rc, "dpk_dgc_sum_forward")
+        ctx.save_for_backward(x, weight, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, out = ctx.saved_tensors
+        g = _f32c(g)
+        b, cin, h, w = x.shape
+        cout = weight.shape[0]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.zeros_like(weight) if ctx.needs_input_grad[1] else None
+        scratch = torch.empty(3 * weight.numel(), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_dgc_sum_backward(_ptr(x), _ptr(weight), _ptr(out), _ptr(g), b, cin, cout, h * w, _ptr(gx),
+                                                 _ptr(gw), _ptr(scratch), _stream(x.device))
+        _lib.check(rc, "dpk_dgc_sum_backward")
+        return gx, gw
+
+
+class _Root(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x, weight = _f32c(x), _f32c(weight)
+        b = x.shape[0]
+        flat = x.reshape(b, -1)
+        c, q = weight.shape
+        out = torch.empty(b, c, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(weight.numel(), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_dgc_root_forward(_ptr(flat), _ptr(weight), b, q, c, _ptr(out), _ptr(scratch), _stream(x.device))
+        _lib.check(rc, "dpk_dgc_root_forward")
+        ctx.save_for_backward(flat, weight, out)
+        ctx.in_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        flat, weight, out = ctx.saved_tensors
+        g = _f32c(g)
+        b = flat.shape[0]
+        c, q = weight.shape
+        gx = torch.empty_like(flat) if ctx.needs_input_grad[0] else None
+        gw = torch.zeros_like(weight) if ctx.needs_input_grad[1] else None
+        scratch = torch.empty(2 * weight.numel(), dtype=torch.float32, device=flat.device)
+        with torch.cuda.device(flat.device):
+            rc = _lib.lib().dpk_dgc_root_backward(_ptr(flat), _ptr(weight), _ptr(out), _ptr(g), b, q, c, _ptr(gx), _ptr(gw),
+                                                  _ptr(scratch), _stream(flat.device))
+        _lib.check(rc, "dpk_dgc_root_backward")
+        return (gx.reshape(ctx.in_shape) if gx is not None else None), gw
+
+
+def leaf(x, loc, scale):
+    x = _check4d(x, "SpatialGaussianLayer.forward")
+    return _Leaf.apply(x, loc, scale)
+
+
+def product(x, desc):
+    x = _check4d(x, "SpatialProductLayer.forward")
+    return _Product.apply(x, desc)
+
+
+def mixture(x, weight):
+    x = _check4d(x, "SpatialSumLayer.forward")
+    return _Sum.apply(x, weight)
+
+
+def root(x, weight):
+    _lib.require_cuda(x, "SpatialRootLayer.forward")
+    return _Root.apply(x, weight)

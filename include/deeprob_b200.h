@@ -131,6 +131,47 @@ int dpk_outer_sum_forward(const float* x, int64_t batch, int32_t partitions, int
 int dpk_mixture_forward(const float* x, const float* weight, int64_t batch, int32_t partitions,
                         int32_t in_nodes, int32_t out_nodes, float* out, float* scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * DGC-SPN layers (deeprob/spn/layers/dgcspn.py), NCHW fp32 like the reference.  Backward entry
+ * points: grad_x is OVERWRITTEN (may be NULL = not wanted), parameter gradients are ACCUMULATED INTO.
+ * ---------------------------------------------------------------------------------------------- */
+/* SpatialGaussianLayer.forward (dgcspn.py:101-120): x (B,Cin,H,W); loc, scale (K,Cin,H,W) -> out (B,K,H,W) */
+int dpk_dgc_leaf_forward(const float* x, const float* loc, const float* scale, int64_t batch,
+                         int32_t in_channels, int32_t out_channels, int32_t hw, float* out, void* stream);
+int dpk_dgc_leaf_backward(const float* x, const float* loc, const float* scale, const float* grad_out,
+                          int64_t batch, int32_t in_channels, int32_t out_channels, int32_t hw, float* grad_x,
+                          float* grad_loc, float* grad_scale, void* stream);
+
+/* SpatialProductLayer.forward (dgcspn.py:224-236): zero pad (pad_left/pad_top; right/bottom implied by the
+ * output size) + 2x2 conv with all-ones depthwise kernels, or the one-hot "all combinations" kernels
+ * (out_channels = channels^4, dgcspn.py:187-193) when depthwise == 0. */
+typedef struct dpk_dgc_product_desc {
+  int32_t channels, height, width;             /* input  (C, H, W) */
+  int32_t out_channels, out_height, out_width; /* output (C | C^4, OH, OW) */
+  int32_t pad_top, pad_left;
+  int32_t stride_h, stride_w, dilation_h, dilation_w;
+  int32_t depthwise;
+} dpk_dgc_product_desc;
+int dpk_dgc_product_forward(const dpk_dgc_product_desc* desc, const float* x, int64_t batch, float* out, void* stream);
+int dpk_dgc_product_backward(const dpk_dgc_product_desc* desc, const float* grad_out, int64_t batch, float* grad_x,
+                             void* stream);
+
+/* SpatialSumLayer.forward (dgcspn.py:289-304): x (B,Cin,H,W), weight (Cout,Cin,H,W) raw logits ->
+ * out (B,Cout,H,W).  scratch: 2*Cout*Cin*HW floats (forward), 3*Cout*Cin*HW floats (backward). */
+int dpk_dgc_sum_forward(const float* x, const float* weight, int64_t batch, int32_t in_channels,
+                        int32_t out_channels, int32_t hw, float* out, float* scratch, void* stream);
+int dpk_dgc_sum_backward(const float* x, const float* weight, const float* out, const float* grad_out,
+                         int64_t batch, int32_t in_channels, int32_t out_channels, int32_t hw, float* grad_x,
+                         float* grad_weight, float* scratch, void* stream);
+
+/* SpatialRootLayer.forward (dgcspn.py:343-355): x (B, Q = C*H*W), weight (classes, Q) -> out (B, classes).
+ * scratch: classes*Q floats (forward), 2*classes*Q floats (backward). */
+int dpk_dgc_root_forward(const float* x, const float* weight, int64_t batch, int64_t features,
+                         int32_t out_classes, float* out, float* scratch, void* stream);
+int dpk_dgc_root_backward(const float* x, const float* weight, const float* out, const float* grad_out,
+                          int64_t batch, int64_t features, int32_t out_classes, float* grad_x,
+                          float* grad_weight, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,28 @@ def make_ratspn():
         print("ratspn", name, "ll[:3]=", rec["ll"].reshape(-1)[:3])
 
 
+def make_dgcspn():
+    from deeprob.spn.models.dgcspn import DgcSpn
+    for name, cfg in pg.DGCSPN_CASES.items():
+        torch.manual_seed(0)
+        model = DgcSpn(**pg.dgcspn_ctor_kwargs(cfg)).eval()
+        names = [k for k, _ in model.named_parameters()]
+        model.load_state_dict(pg.dgcspn_fill_state(model.state_dict(), names, cfg))
+        model.base_layer.scale.requires_grad_(True)
+        x, g = pg.dgcspn_inputs(cfg)
+        xg = x.clone().requires_grad_(True)
+        out = model(xg)
+        (out * g).sum().backward()
+        rec = {"ll": _np(out)}
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                v = _np(p.grad)
+                rec["grad." + k] = v if v.size <= 20000 else v.reshape(-1)[:: max(1, v.size // 4096)]
+        rec["grad.x"] = _np(torch.nan_to_num(xg.grad))[:4]
+        np.savez_compressed(os.path.join(GOLDEN, "dgcspn_%s.npz" % name), **rec)
+        print("dgcspn", name, "ll[:3]=", rec["ll"].reshape(-1)[:3])
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLDEN, exist_ok=True)

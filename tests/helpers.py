@@ -51,3 +51,27 @@ def product_model(cfg, device, seed=0, scale_grad=True):
     if cfg["kind"] == "gaussian" and scale_grad:
         model.base_layer.scale.requires_grad_(True)     # also exercises d/dscale; disables the unit-scale kernels
     return model.to(device)
+
+
+# ---- DGC-SPN -------------------------------------------------------------------------------------
+def dgc_oracle_for(cfg, seed=0):
+    from oracle.dgcspn_oracle import DgcSpnOracle
+    kw = pg.dgcspn_ctor_kwargs(cfg)
+    kw.pop("optimize_scale")
+    orc = DgcSpnOracle(**kw)
+    k, (c, h, w) = cfg["n_batch"], cfg["in_features"]
+    state = {"base_layer.loc": torch.zeros(k, c, h, w), "base_layer.scale": torch.ones(k, c, h, w)}
+    for i, shp in enumerate(orc.sum_shapes):      # (C_out, C_in, H, W)
+        state["layers.%d.weight" % (2 * i + 1)] = torch.zeros(*shp)
+    state["root_layer.weight"] = torch.zeros(cfg["out_classes"], int(np.prod(orc.root_in)))
+    state = pg.dgcspn_fill_state(state, list(state.keys()), cfg, seed)
+    return orc.load_reference_state(state), state
+
+
+def dgc_product_model(cfg, device, seed=0):
+    from deeprob_kit_b200.spn.models import DgcSpn
+    model = DgcSpn(**pg.dgcspn_ctor_kwargs(cfg)).eval()
+    names = [k for k, _ in model.named_parameters()]
+    model.load_state_dict(pg.dgcspn_fill_state(model.state_dict(), names, cfg, seed))
+    model.base_layer.scale.requires_grad_(True)
+    return model.to(device)

@@ -83,3 +83,58 @@ def ratspn_inputs(cfg, seed=0):
         x[0, :] = np.nan              # one fully marginalised row: LL must be ~0
     g = rng.standard_normal((b, cfg["out_classes"])).astype(np.float32)
     return torch.from_numpy(x), torch.from_numpy(g)
+
+
+# ------------------------------------------------------------------------------------------------
+# DGC-SPN cases (constructor kwargs of deeprob/spn/models/dgcspn.py:16-29)
+# ------------------------------------------------------------------------------------------------
+DGCSPN_CASES = {
+    "dw8": dict(in_features=(1, 8, 8), out_classes=1, n_batch=4, sum_channels=4, depthwise=True, n_pooling=0,
+                optimize_scale=False, batch=24, nan_frac=0.0),
+    "full8": dict(in_features=(2, 8, 8), out_classes=3, n_batch=2, sum_channels=2, depthwise=False, n_pooling=1,
+                  optimize_scale=True, batch=20, nan_frac=0.25),
+    "mixed16": dict(in_features=(3, 16, 16), out_classes=2, n_batch=4, sum_channels=5, depthwise=[False, True],
+                    n_pooling=2, optimize_scale=True, batch=12, nan_frac=0.0),
+    # BASELINE config 3 structure on a small batch
+    "mnist": dict(in_features=(1, 28, 28), out_classes=1, n_batch=8, sum_channels=8, depthwise=True, n_pooling=0,
+                  optimize_scale=False, batch=16, nan_frac=0.0),
+    "mnist_pool": dict(in_features=(1, 28, 28), out_classes=10, n_batch=16, sum_channels=32, depthwise=True, n_pooling=2,
+                       optimize_scale=True, batch=8, nan_frac=0.1),
+}
+
+
+def dgcspn_ctor_kwargs(cfg):
+    kw = {k: cfg[k] for k in ("in_features", "out_classes", "n_batch", "sum_channels", "n_pooling", "optimize_scale")}
+    dw = cfg["depthwise"]
+    kw["depthwise"] = list(dw) if isinstance(dw, (list, tuple)) else dw
+    return kw
+
+
+def dgcspn_fill_state(state, param_names, cfg, seed=0):
+    """Overwrite the learnable tensors (keys in `param_names`) of a reference-keyed state_dict."""
+    rng = np.random.RandomState(3000 + seed)
+    out = dict(state)
+    for key in sorted(param_names):
+        shape = tuple(state[key].shape)
+        if key == "base_layer.loc":
+            v = rng.standard_normal(shape).astype(np.float32)
+        elif key == "base_layer.scale":
+            v = (0.4 + 0.8 * rng.random_sample(shape)).astype(np.float32) if cfg["optimize_scale"] else np.ones(shape, np.float32)
+        elif key == "root_layer.weight":
+            v = _log_dirichlet(rng, shape) + np.float32(0.3)
+        else:   # spatial sum layer (C_out, C_in, H, W): Dirichlet over dim 1 + a per-(o,h,w) shift
+            g = rng.gamma(1.0, 1.0, size=shape) + 1e-12
+            v = (np.log(g / g.sum(1, keepdims=True)) + rng.standard_normal((shape[0], 1, *shape[2:]))).astype(np.float32)
+        out[key] = torch.from_numpy(v)
+    return out
+
+
+def dgcspn_inputs(cfg, seed=0):
+    rng = np.random.RandomState(4000 + seed)
+    shape = (cfg["batch"], *cfg["in_features"])
+    x = rng.standard_normal(shape).astype(np.float32)
+    if cfg["nan_frac"] > 0:
+        x[rng.random_sample(shape) < cfg["nan_frac"]] = np.nan
+        x[0] = np.nan
+    g = rng.standard_normal((cfg["batch"], cfg["out_classes"])).astype(np.float32)
+    return torch.from_numpy(x), torch.from_numpy(g)

@@ -1,0 +1,83 @@
+"""GPU parity of the CUDA DGC-SPN layers against the CPU oracle and the reference golden vectors."""
+import pytest
+import torch
+
+import param_gen as pg
+from conftest import load_golden, norm_err, rel_err
+from helpers import dgc_oracle_for, dgc_product_model, subsample_like
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("name", sorted(pg.DGCSPN_CASES))
+def test_log_prob_and_gradients(name):
+    cfg = pg.DGCSPN_CASES[name]
+    model = dgc_product_model(cfg, DEV)
+    orc, _ = dgc_oracle_for(cfg)
+    x, g = pg.dgcspn_inputs(cfg)
+    gold = load_golden("dgcspn_" + name)
+    with torch.enable_grad():
+        xd = x.to(DEV).requires_grad_(True)
+        out = model(xd)
+        (out * g.to(DEV)).sum().backward()
+    assert out.shape == (cfg["batch"], cfg["out_classes"])
+    assert rel_err(out.detach().cpu(), orc.log_prob(x)) < TOL
+    assert rel_err(out.detach().cpu(), gold["ll"]) < TOL
+    truth = dgc_oracle_for(cfg)[0].double().grads(x.double(), g.double(), clean_nan=True)
+    gtol = TOL + 4e-7 * float(out.abs().max())
+    sums = [l.weight.grad for l in model.layers if l.__class__.__name__ == "SpatialSumLayer"]
+    assert norm_err(model.base_layer.loc.grad, truth["loc"]) < gtol
+    assert norm_err(model.base_layer.scale.grad, truth["scale"]) < gtol
+    assert norm_err(model.root_layer.weight.grad, truth["root"]) < gtol
+    for a, b in zip(sums, truth["sums"]):
+        assert norm_err(a, b) < gtol
+    assert norm_err(torch.nan_to_num(xd.grad.cpu()), torch.nan_to_num(truth["x"])) < gtol
+    if cfg["nan_frac"] == 0:
+        assert norm_err(subsample_like(model.base_layer.loc.grad.cpu(), gold["grad.base_layer.loc"].size),
+                        gold["grad.base_layer.loc"].reshape(-1)) < 2 * gtol
+
+
+def test_product_of_ones_and_shapes():
+    """deeprob-kit tests/test_dgcspn.py:46-75: inside the valid region a 2x2 product of ones is 4."""
+    from deeprob_kit_b200.spn.layers.dgcspn import SpatialProductLayer
+    ones = torch.ones(8, 3, 32, 32, device=DEV)
+    p = SpatialProductLayer((3, 32, 32), kernel_size=2, padding='full', stride=1, dilation=4, depthwise=True)
+    assert torch.allclose(p(ones)[:, :, 4:-4, 4:-4], torch.tensor(4.0, device=DEV))
+    p = SpatialProductLayer((3, 32, 32), kernel_size=2, padding='valid', stride=2, dilation=1, depthwise=True)
+    out = p(ones)
+    assert out.shape == (8, 3, 16, 16) and torch.allclose(out, torch.tensor(4.0, device=DEV))
+    p = SpatialProductLayer((3, 32, 32), kernel_size=2, padding='full', stride=1, dilation=8, depthwise=False).to(DEV)
+    out = p(ones)
+    assert out.shape == (8, 81, 40, 40)
+    assert torch.allclose(out[:, :, 8:-8, 8:-8], torch.tensor(4.0, device=DEV))
+
+
+@pytest.mark.parametrize("n_pooling,depthwise", [(0, False), (2, False), (0, True), (2, True)])
+def test_mpe_improves_log_prob(n_pooling, depthwise):
+    """deeprob-kit tests/test_dgcspn.py:89-96."""
+    from deeprob_kit_b200.spn.models import DgcSpn
+    torch.manual_seed(42)
+    data = torch.randn(8, 3, 32, 32)
+    mar = data.clone()
+    mar[torch.rand_like(mar) < 0.5] = float("nan")
+    model = DgcSpn((3, 32, 32), n_batch=4, sum_channels=4, n_pooling=n_pooling, depthwise=depthwise).to(DEV)
+    lls = model.log_prob(data.to(DEV))
+    with torch.enable_grad():
+        mpe = model.mpe(mar.to(DEV))
+    assert torch.all(model.log_prob(mpe).squeeze() > lls.squeeze())
+
+
+def test_config3_batch_properties():
+    """BASELINE config 3 structure at a larger batch: slice/permutation invariance + marginalisation to 1."""
+    cfg = dict(pg.DGCSPN_CASES["mnist"])
+    model = dgc_product_model(cfg, DEV)
+    orc, _ = dgc_oracle_for(cfg)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(1030, 1, 28, 28, generator=gen)
+    out = model(x.to(DEV))
+    assert torch.equal(model(x[100:164].to(DEV)), out[100:164])
+    idx = torch.arange(0, 1030, 41)
+    assert rel_err(out[idx.to(DEV)].cpu(), orc.log_prob(x[idx])) < TOL
+    assert float(model(torch.full((3, 1, 28, 28), float("nan"), device=DEV)).abs().max()) < 1e-3
