@@ -111,6 +111,11 @@ class DgcProductDesc(ctypes.Structure):
                                      "depthwise")]
 
 
+class CouplingDesc(ctypes.Structure):
+    _fields_ = [("batch", c_i64), ("features", c_i32), ("affine", c_i32), ("direction", c_i32), ("w_count", c_i32),
+                ("w_inner", c_i32), ("x_stride", c_i64), ("z_stride", c_i64), ("inv_mask", c_vp), ("scale_weight", c_vp)]
+
+
 # name -> (restype, argtypes); every symbol include/deeprob_b200.h declares must be listed here
 # (tests/test_cabi.py cross-checks this table against the header and the built library).
 SIGNATURES = {
@@ -134,6 +139,16 @@ SIGNATURES = {
     "dpk_dgc_sum_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dpk_dgc_sum_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dpk_dgc_root_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "dpk_coupling_forward": (ctypes.c_int, [ctypes.POINTER(CouplingDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "dpk_coupling_backward": (ctypes.c_int, [ctypes.POINTER(CouplingDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64,
+                                             c_vp, c_i64, c_vp, c_vp]),
+    "dpk_feature_reduce": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
+    "dpk_feature_affine": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    "dpk_flow_preprocess_forward": (ctypes.c_int, [c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "dpk_flow_preprocess_backward": (ctypes.c_int, [c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp, c_i64,
+                                                    c_i32, c_vp]),
+    "dpk_normal_prior_forward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "dpk_normal_prior_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "dpk_dgc_root_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 

@@ -1,0 +1,232 @@
+"""ctypes glue + autograd Functions of the flow bijectors (csrc/flows.cu)."""
+import ctypes
+
+import torch
+
+from .. import _lib
+from ..spn._engine import _PTR, _f32c, _ptr
+
+
+def _stream(dev):
+    return _PTR(_lib.stream_ptr(dev))
+
+
+def _coupling_desc(batch, n, affine, direction, w, w_inner, x_stride, z_stride, inv_mask):
+    d = _lib.CouplingDesc()
+    d.batch, d.features, d.affine, d.direction = batch, n, 1 if affine else 0, direction
+    d.w_count = w.numel() if w is not None else 1
+    d.w_inner = w_inner
+    d.x_stride, d.z_stride = x_stride, z_stride
+    d.inv_mask = inv_mask.data_ptr() if inv_mask is not None else None
+    d.scale_weight = w.data_ptr() if w is not None else None
+    return d
+
+
+class _Coupling(torch.autograd.Function):
+    """(x, z, w) -> (out, log_det).  `offset`/`n` select the transformed slice of every sample row; the rest of
+    the row passes through unchanged (channel-wise couplings)."""
+
+    @staticmethod
+    def forward(ctx, x, z, w, inv_mask, n, offset, affine, direction, w_inner):
+        _lib.require_cuda(x, "coupling layer")
+        x, z = _f32c(x), _f32c(z)
+        w = _f32c(w).reshape(-1) if w is not None else None
+        batch = x.shape[0]
+        row = x[0].numel() if batch else n
+        out = torch.empty_like(x) if n == row else x.clone()
+        ldj = torch.zeros(batch, dtype=torch.float32, device=x.device)
+        d = _coupling_desc(batch, n, affine, direction, w, w_inner, row, z[0].numel() if batch else 2 * n, inv_mask)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_coupling_forward(ctypes.byref(d), _PTR(x.data_ptr() + 4 * offset), _ptr(z),
+                                                 _PTR(out.data_ptr() + 4 * offset), row, _ptr(ldj), _stream(x.device))
+        _lib.check(rc, "dpk_coupling_forward")
+        ctx.save_for_backward(x, z, w if w is not None else x.new_empty(0), inv_mask if inv_mask is not None else x.new_empty(0))
+        ctx.cfg = (n, offset, affine, direction, w_inner, row)
+        return out, ldj
+
+    @staticmethod
+    def backward(ctx, gout, gldj):
+        x, z, w, inv_mask = ctx.saved_tensors
+        n, offset, affine, direction, w_inner, row = ctx.cfg
+        w = w if w.numel() else None
+        inv_mask = inv_mask if inv_mask.numel() else None
+        gout = _f32c(gout)
+        batch = x.shape[0]
+        gx = torch.empty_like(x) if n == row else gout.clone()
+        gz = torch.empty_like(z)
+        gw = torch.zeros_like(w) if (w is not None and ctx.needs_input_grad[2]) else None
+        gl = _f32c(gldj) if gldj is not None else None
+        d = _coupling_desc(batch, n, affine, direction, w, w_inner, row, z[0].numel() if batch else 2 * n, inv_mask)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_coupling_backward(
+                ctypes.byref(d), _PTR(x.data_ptr() + 4 * offset), _ptr(z), _PTR(gout.data_ptr() + 4 * offset), row,
+                _ptr(gl), _PTR(gx.data_ptr() + 4 * offset), row, _ptr(gz), z[0].numel() if batch else 2 * n, _ptr(gw),
+                _stream(x.device))
+        _lib.check(rc, "dpk_coupling_backward")
+        return gx, gz, gw, None, None, None, None, None, None
+
+
+def coupling(x, z, w, inv_mask, n, offset, affine, direction, w_inner):
+    return _Coupling.apply(x, z, w, inv_mask, n, offset, affine, direction, w_inner)
+
+
+# ------------------------------------------------------------------------------------------------
+# batch-norm bijector
+# ------------------------------------------------------------------------------------------------
+def _feature_reduce(x, center, other, features, inner, mode):
+    s = torch.zeros(features, dtype=torch.float32, device=x.device)
+    d = torch.zeros(features, dtype=torch.float32, device=x.device) if mode == 2 else None
+    batch = x.shape[0]
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dpk_feature_reduce(_ptr(x), _ptr(center), _ptr(other), _ptr(s), _ptr(d), batch, features, inner,
+                                           mode, _stream(x.device))
+    _lib.check(rc, "dpk_feature_reduce")
+    return s, d
+
+
+def _feature_affine(x, a, c, features, inner, y=None, k=None, mu=None):
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dpk_feature_affine(_ptr(x), _ptr(a), _ptr(c), _ptr(y), _ptr(k), _ptr(mu), _ptr(out), x.shape[0],
+                                           features, inner, _stream(x.device))
+    _lib.check(rc, "dpk_feature_affine")
+    return out
+
+
+class _BatchNorm(torch.autograd.Function):
+    """u = (x - mean) / sqrt(var + eps) * exp(weight) + bias, log_det = sum(weight - log(var+eps)/2) * inner.
+    direction 1 is the inverse map (always with the running statistics)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, unbiased, direction):
+        _lib.require_cuda(x, "batch-norm bijector")
+        x = _f32c(x)
+        batch, features = x.shape[0], x.shape[1]
+        inner = x[0, 0].numel() if x.dim() > 2 else 1
+        n = batch * inner
+        w, b = weight.detach().reshape(-1).float(), bias.detach().reshape(-1).float()
+        use_batch = training and direction == 0
+        if use_batch:
+            s, _ = _feature_reduce(x, None, None, features, inner, 0)
+            mean = s / n
+            m2, _ = _feature_reduce(x, mean, None, features, inner, 1)
+            var = m2 / (n - 1 if unbiased else n)
+            with torch.no_grad():
+                running_var.mul_(momentum).add_(var.view_as(running_var) * (1.0 - momentum))
+                running_mean.mul_(momentum).add_(mean.view_as(running_mean) * (1.0 - momentum))
+        else:
+            mean, var = running_mean.reshape(-1).float(), running_var.reshape(-1).float()
+        veps = var + eps
+        if direction == 0:
+            a = torch.rsqrt(veps) * torch.exp(w)
+            c = b - mean * a
+            ldj = torch.sum(w - 0.5 * torch.log(veps)) * inner
+        else:
+            a = torch.sqrt(veps) * torch.exp(-w)
+            c = mean - b * a
+            ldj = torch.sum(0.5 * torch.log(veps) - w) * inner
+        out = _feature_affine(x, a.contiguous(), c.contiguous(), features, inner)
+        ctx.save_for_backward(x, w, b, mean, veps, a)
+        ctx.cfg = (use_batch, unbiased, direction, inner, features, n, weight.shape)
+        return out, ldj.expand(batch)
+
+    @staticmethod
+    def backward(ctx, gout, gldj):
+        x, w, b, mean, veps, a = ctx.saved_tensors
+        use_batch, unbiased, direction, inner, features, n, wshape = ctx.cfg
+        gout = _f32c(gout)
+        gi = gldj.sum() if gldj is not None else gout.new_zeros(())
+        if direction == 0:
+            s1, s2 = _feature_reduce(x, mean.contiguous(), gout, features, inner, 2)   # sum g, sum g*(x-mean)
+            gw = s2 * a + gi * inner
+            gb = s1
+            if use_batch:
+                gv = s2 * torch.exp(w) * (-0.5) * veps.pow(-1.5) + gi * inner * (-0.5) / veps
+                gmu = -a * s1
+                denom = (n - 1) if unbiased else n
+                gx = _feature_affine(gout, a.contiguous(), (gmu / n).contiguous(), features, inner, y=x,
+                                     k=(2.0 * gv / denom).contiguous(), mu=mean.contiguous())
+            else:
+                gx = _feature_affine(gout, a.contiguous(), torch.zeros_like(a), features, inner)
+        else:   # x_out = (u - b) * a + mean,  a = sqrt(veps) * exp(-w)
+            s1, s2 = _feature_reduce(x, b.contiguous(), gout, features, inner, 2)       # sum g, sum g*(u-b)
+            gw = -s2 * a - gi * inner
+            gb = -s1 * a
+            gx = _feature_affine(gout, a.contiguous(), torch.zeros_like(a), features, inner)
+        return gx, gw.reshape(wshape), gb.reshape(wshape), None, None, None, None, None, None, None
+
+
+def batch_norm(x, weight, bias, running_mean, running_var, training, momentum, eps, unbiased, direction=0):
+    return _BatchNorm.apply(x, weight, bias, running_mean, running_var, training, momentum, eps, unbiased, direction)
+
+
+# ------------------------------------------------------------------------------------------------
+# preprocessing and prior
+# ------------------------------------------------------------------------------------------------
+class _Preprocess(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, noise, bins, alpha):
+        _lib.require_cuda(x, "flow preprocessing")
+        x = _f32c(x)
+        batch = x.shape[0]
+        n = x[0].numel() if batch else 1
+        out = torch.empty_like(x)
+        ildj = torch.zeros(batch, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_flow_preprocess_forward(_ptr(x), _ptr(noise), float(bins), float(alpha), _ptr(out),
+                                                        _ptr(ildj), batch, n, _stream(x.device))
+        _lib.check(rc, "dpk_flow_preprocess_forward")
+        ctx.save_for_backward(x, noise if noise is not None else x.new_empty(0))
+        ctx.cfg = (bins, alpha, n)
+        return out, ildj
+
+    @staticmethod
+    def backward(ctx, gout, gildj):
+        x, noise = ctx.saved_tensors
+        bins, alpha, n = ctx.cfg
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_flow_preprocess_backward(_ptr(x), _ptr(noise if noise.numel() else None), float(bins),
+                                                         float(alpha), _ptr(_f32c(gout)),
+                                                         _ptr(_f32c(gildj) if gildj is not None else None), _ptr(gx),
+                                                         x.shape[0], n, _stream(x.device))
+        _lib.check(rc, "dpk_flow_preprocess_backward")
+        return gx, None, None, None
+
+
+def preprocess(x, noise, bins, alpha):
+    return _Preprocess.apply(x, noise, bins, alpha)
+
+
+class _NormalPrior(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, ildj, loc, scale):
+        _lib.require_cuda(z, "flow prior")
+        z = _f32c(z)
+        batch = z.shape[0]
+        n = z[0].numel() if batch else 1
+        out = torch.empty(batch, dtype=torch.float32, device=z.device)
+        il = _f32c(ildj) if isinstance(ildj, torch.Tensor) else None
+        with torch.cuda.device(z.device):
+            rc = _lib.lib().dpk_normal_prior_forward(_ptr(z), _ptr(loc), _ptr(scale), _ptr(il), _ptr(out), batch, n,
+                                                     _stream(z.device))
+        _lib.check(rc, "dpk_normal_prior_forward")
+        ctx.save_for_backward(z, loc if loc is not None else z.new_empty(0), scale if scale is not None else z.new_empty(0))
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, loc, scale = ctx.saved_tensors
+        gout = _f32c(gout)
+        gz = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            rc = _lib.lib().dpk_normal_prior_backward(_ptr(z), _ptr(loc if loc.numel() else None),
+                                                      _ptr(scale if scale.numel() else None), _ptr(gout), _ptr(gz),
+                                                      z.shape[0], ctx.n, _stream(z.device))
+        _lib.check(rc, "dpk_normal_prior_backward")
+        return gz, (gout if ctx.needs_input_grad[1] else None), None, None
+
+
+def normal_prior(z, ildj, loc, scale):
+    return _NormalPrior.apply(z, ildj, loc, scale)

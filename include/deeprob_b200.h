@@ -172,6 +172,58 @@ int dpk_dgc_root_backward(const float* x, const float* weight, const float* out,
                           int64_t batch, int64_t features, int32_t out_classes, float* grad_x,
                           float* grad_weight, float* scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Normalizing-flow bijectors (deeprob/flows).  Rows are per-sample flattened (B, N) arrays with an
+ * explicit row stride, so channel-wise halves of a (B,C,H,W) tensor can be passed without a copy.
+ * ---------------------------------------------------------------------------------------------- */
+/* Affine coupling transform + log-det (CouplingLayer1d coupling.py:72-104, CouplingLayer2d :179-272,
+ * AutoregressiveLayer autoregressive.py:72-79).  z = conditioner output rows: t = z[0:N], raw scale =
+ * z[N:2N]; s = inv_mask * w * tanh(raw) with w = scale_weight[(e / w_inner) % w_count] (ScaledTanh,
+ * torch/utils.py:52-70).  direction 0: out = (x - inv_mask*t) * exp(-s), log_det -= sum s ("backward" =
+ * density direction); direction 1: out = x * exp(s) + inv_mask*t, log_det += sum s (sampling direction).
+ * affine == 0: translation only (NICE), log_det untouched. */
+typedef struct dpk_coupling_desc {
+  int64_t batch;
+  int32_t features;          /* N: transformed elements per sample */
+  int32_t affine;
+  int32_t direction;
+  int32_t w_count, w_inner;  /* ScaledTanh weight broadcast pattern */
+  int64_t x_stride, z_stride;
+  const float* inv_mask;     /* (N) or NULL (= ones) */
+  const float* scale_weight; /* (w_count) */
+} dpk_coupling_desc;
+int dpk_coupling_forward(const dpk_coupling_desc* desc, const float* x, const float* z, float* out,
+                         int64_t out_stride, float* log_det /* (B), accumulated into; may be NULL */, void* stream);
+/* grad_x (may be NULL) and grad_z are overwritten; grad_scale_weight (w_count, may be NULL) is accumulated into */
+int dpk_coupling_backward(const dpk_coupling_desc* desc, const float* x, const float* z, const float* grad_out,
+                          int64_t grad_out_stride, const float* grad_log_det, float* grad_x, int64_t grad_x_stride,
+                          float* grad_z, int64_t grad_z_stride, float* grad_scale_weight, void* stream);
+
+/* Building blocks of the batch-norm bijector (flows/utils.py:118-153, 183-221) over (B, F, I) arrays
+ * (1d: I = 1; 2d: I = H*W).  mode 0: sum_out[f] += sum x; mode 1: sum_out[f] += sum (x - center[f])^2;
+ * mode 2: sum_out[f] += sum other, dot_out[f] += sum other * (x - center[f]). */
+int dpk_feature_reduce(const float* x, const float* center, const float* other, float* sum_out, float* dot_out,
+                       int64_t batch, int32_t features, int32_t inner, int32_t mode, void* stream);
+/* out = x * a[f] + c[f]  (+ k[f] * (y - mu[f]) when y != NULL) */
+int dpk_feature_affine(const float* x, const float* a, const float* c, const float* y, const float* k,
+                       const float* mu, float* out, int64_t batch, int32_t features, int32_t inner, void* stream);
+
+/* DequantizeLayer + LogitLayer apply_backward fused (flows/utils.py:244-248, 276-284): q = (x*(bins-1) +
+ * noise)/bins (bins <= 0: q = x), out = logit(alpha + (1-2*alpha)*q) (alpha < 0: out = q);
+ * inv_log_det[b] -= sum (log y + log(1-y)); the constant terms are added by the caller. */
+int dpk_flow_preprocess_forward(const float* x, const float* noise, float bins, float alpha, float* out,
+                                float* inv_log_det, int64_t batch, int32_t features, void* stream);
+int dpk_flow_preprocess_backward(const float* x, const float* noise, float bins, float alpha,
+                                 const float* grad_out, const float* grad_inv_log_det, float* grad_x,
+                                 int64_t batch, int32_t features, void* stream);
+
+/* Prior + final sum (flows/models/base.py:139-143): out[b] = sum_e logN(z[b,e]; loc[e], scale[e]) +
+ * inv_log_det[b]; loc/scale NULL = standard normal. */
+int dpk_normal_prior_forward(const float* z, const float* loc, const float* scale, const float* inv_log_det,
+                             float* out, int64_t batch, int32_t features, void* stream);
+int dpk_normal_prior_backward(const float* z, const float* loc, const float* scale, const float* grad_out,
+                              float* grad_z, int64_t batch, int32_t features, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

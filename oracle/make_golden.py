@@ -88,6 +88,50 @@ def make_dgcspn():
         print("dgcspn", name, "ll[:3]=", rec["ll"].reshape(-1)[:3])
 
 
+def make_flows():
+    from deeprob.flows import models as ref_models
+    import warnings
+    warnings.simplefilter("ignore")
+    for name, cfg in pg.FLOW_CASES.items():
+        torch.manual_seed(0)
+        model = getattr(ref_models, cfg["model"])(**cfg["kw"])
+        model.load_state_dict(pg.flow_fill_state(model.state_dict()))
+        x, g = pg.flow_inputs(cfg)
+        rec = {}
+        if cfg["model"] == "RealNVP2d":        # conv conditioners: keep the whole (small) state in the fixture
+            for k, v in model.state_dict().items():
+                rec["state." + k] = _np(v)
+        model.eval()
+        xg = x.clone().requires_grad_(True)
+        out = model(xg)
+        (out * g).sum().backward()
+        rec["ll"] = _np(out)
+        rec["grad.x"] = _np(xg.grad)[:4]
+        for k, p in model.named_parameters():
+            if p.grad is not None and ("scale_act" in k or p.numel() <= 4096):
+                rec["grad." + k] = _np(p.grad)
+        # invertibility vector (tests/test_flows.py:22-26): apply_forward(apply_backward(x)) == x
+        with torch.no_grad():
+            u, ildj = model.apply_backward(model.preprocess(x)[0])
+            rec["u"] = _np(u)[:4]
+            rec["ildj"] = _np(ildj if isinstance(ildj, torch.Tensor) else torch.full((x.shape[0],), float(ildj)))
+        # training mode: batch statistics in the batch-norm bijectors (+ running-stat update)
+        if any("running_var" in k for k in model.state_dict()) and cfg["model"] != "RealNVP2d":
+            model.zero_grad()
+            model.train()
+            out_t = model(x)
+            (out_t * g).sum().backward()
+            rec["train.ll"] = _np(out_t)
+            for k, v in model.state_dict().items():
+                if k.endswith("running_mean") or k.endswith("running_var"):
+                    rec["train.state." + k] = _np(v)
+            for k, p in model.named_parameters():
+                if p.grad is not None and ("scale_act" in k or p.numel() <= 4096):
+                    rec["train.grad." + k] = _np(p.grad)
+        np.savez_compressed(os.path.join(GOLDEN, "flows_%s.npz" % name), **rec)
+        print("flows", name, "ll[:3]=", rec["ll"][:3])
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLDEN, exist_ok=True)

@@ -75,3 +75,22 @@ def dgc_product_model(cfg, device, seed=0):
     model.load_state_dict(pg.dgcspn_fill_state(model.state_dict(), names, cfg, seed))
     model.base_layer.scale.requires_grad_(True)
     return model.to(device)
+
+
+# ---- flows ------------------------------------------------------------------------------------------
+def flow_reference_state(cfg, name=None):
+    """Reference-keyed parameters of a flow case: 1D models are rebuilt from the product constructors (same
+    keys/shapes/masks as the reference, checked in test_flows_host.py) + the numpy-seeded fill; 2D models
+    read the state stored in their golden fixture (conv conditioners are initialised by torch's RNG)."""
+    from conftest import load_golden
+    from deeprob_kit_b200.flows import models as fm
+    import warnings
+    warnings.simplefilter("ignore")
+    model = getattr(fm, cfg["model"])(**cfg["kw"])
+    if cfg["model"] == "RealNVP2d":
+        gold = load_golden("flows_" + name)
+        state = {k[len("state."):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("state.")}
+    else:
+        state = pg.flow_fill_state(model.state_dict())
+    model.load_state_dict(state)
+    return model, state

@@ -138,3 +138,61 @@ def dgcspn_inputs(cfg, seed=0):
         x[0] = np.nan
     g = rng.standard_normal((cfg["batch"], cfg["out_classes"])).astype(np.float32)
     return torch.from_numpy(x), torch.from_numpy(g)
+
+
+# ------------------------------------------------------------------------------------------------
+# Flow cases (constructor kwargs of deeprob/flows/models/realnvp.py:17-28,76-87 and maf.py:13-26)
+# ------------------------------------------------------------------------------------------------
+FLOW_CASES = {
+    "nvp1d_small": dict(model="RealNVP1d", kw=dict(in_features=10, n_flows=3, depth=2, units=16), batch=48, unit_x=False),
+    "nvp1d_nice": dict(model="RealNVP1d", kw=dict(in_features=9, n_flows=4, depth=1, units=12, batch_norm=False, affine=False),
+                       batch=40, unit_x=False),
+    "nvp1d_logit": dict(model="RealNVP1d", kw=dict(in_features=12, n_flows=2, depth=1, units=16, logit=0.05), batch=32,
+                        unit_x=True),
+    # BASELINE config 4 (primary): 8 affine couplings with MLP conditioners on flattened 32x32x3
+    "nvp1d_cifar": dict(model="RealNVP1d", kw=dict(in_features=3072, n_flows=8, depth=2, units=512), batch=24, unit_x=True),
+    "maf_seq": dict(model="MAF", kw=dict(in_features=10, n_flows=2, depth=2, units=16), batch=48, unit_x=False),
+    "maf_rand": dict(model="MAF", kw=dict(in_features=7, n_flows=3, depth=1, units=20, activation="tanh", sequential=False,
+                                          random_state=42, batch_norm=False), batch=32, unit_x=False),
+    "nvp2d_res": dict(model="RealNVP2d", kw=dict(in_features=(3, 8, 8), n_flows=1, n_blocks=1, channels=4), batch=12,
+                      unit_x=False),
+    "nvp2d_dense": dict(model="RealNVP2d", kw=dict(in_features=(2, 8, 8), network="densenet", n_flows=1, n_blocks=1, channels=4,
+                                                   logit=0.1), batch=10, unit_x=True),
+}
+
+
+def flow_fill_state(state, seed=0):
+    """Perturb a freshly initialised flow state_dict so that every term is exercised: ScaledTanh weights are
+    zero-initialised (log-det == 0 at init, deeprob/torch/utils.py:61) and the batch-norm statistics are trivial."""
+    rng = np.random.RandomState(5000 + seed)
+    out = {}
+    for key in sorted(state.keys()):
+        t = state[key]
+        shape = tuple(t.shape)
+        name = key.split(".")[-1]
+        if "scale_act" in key:
+            v = 0.2 + 0.8 * rng.random_sample(shape)
+        elif name == "running_var":
+            v = 0.5 + rng.random_sample(shape)
+        elif name == "running_mean":
+            v = 0.3 * rng.standard_normal(shape)
+        elif name in ("weight", "bias") and t.dim() in (2, 4) and shape[0] == 1:      # batch-norm bijector (1,F[,1,1])
+            v = 0.2 * rng.standard_normal(shape)
+        elif name == "weight" and t.dim() == 2 and "network" in key:                   # Linear / MaskedLinear
+            v = rng.standard_normal(shape) * (0.7 / np.sqrt(shape[1]))
+        elif name == "bias" and "network" in key and t.dim() == 1 and "conv" not in key:
+            v = 0.1 * rng.standard_normal(shape)
+        else:
+            out[key] = t
+            continue
+        out[key] = torch.from_numpy(np.asarray(v, dtype=np.float32)).reshape(shape)
+    return out
+
+
+def flow_inputs(cfg, seed=0):
+    rng = np.random.RandomState(6000 + seed)
+    feats = cfg["kw"]["in_features"]
+    shape = (cfg["batch"],) + (tuple(feats) if isinstance(feats, tuple) else (feats,))
+    x = rng.random_sample(shape) if cfg["unit_x"] else rng.standard_normal(shape)
+    g = rng.standard_normal((cfg["batch"],))
+    return torch.from_numpy(x.astype(np.float32)), torch.from_numpy(g.astype(np.float32))
