@@ -30,6 +30,7 @@ class _Coupling(torch.autograd.Function):
     def forward(ctx, x, z, w, inv_mask, n, offset, affine, direction, w_inner):
         _lib.require_cuda(x, "coupling layer")
         x, z = _f32c(x), _f32c(z)
+        ctx.w_shape = w.shape if w is not None else None
         w = _f32c(w).reshape(-1) if w is not None else None
         batch = x.shape[0]
         row = x[0].numel() if batch else n
@@ -63,6 +64,8 @@ class _Coupling(torch.autograd.Function):
                 _ptr(gl), _PTR(gx.data_ptr() + 4 * offset), row, _ptr(gz), z[0].numel() if batch else 2 * n, _ptr(gw),
                 _stream(x.device))
         _lib.check(rc, "dpk_coupling_backward")
+        if gw is not None:
+            gw = gw.reshape(ctx.w_shape)
         return gx, gz, gw, None, None, None, None, None, None
 
 

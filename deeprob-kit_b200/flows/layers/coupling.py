@@ -58,6 +58,10 @@ class CouplingLayer2d(Bijector):
         self.affine = affine
         self.channelwise = channelwise
         self.reverse = reverse
+        # cuDNN would otherwise run the fp32 conditioner convolutions (forward AND backward) on TF32 tensor
+        # cores (10-bit mantissa); the 1e-4 parity bar of the log-likelihood needs true fp32.  The backward runs
+        # later inside autograd, so a scoped flag cannot cover it: the process-wide switch is turned off here.
+        torch.backends.cudnn.allow_tf32 = False
         if not channelwise:
             mask, inv_mask = self.build_checkerboard_masks()
             if reverse:
@@ -95,6 +99,9 @@ class CouplingLayer2d(Bijector):
         mask = np.sum(np.indices([1, self.in_height, self.in_width]), axis=0) % 2
         return mask, 1.0 - mask
 
+    def _conditioner(self, x):
+        return self.network(x)
+
     def _transform(self, x, direction):
         hw = self.in_height * self.in_width
         w = self.scale_act.weight if self.affine else None
@@ -103,10 +110,10 @@ class CouplingLayer2d(Bijector):
             first, second = torch.chunk(x, chunks=2, dim=1)
             cond = first if self.reverse else second           # untouched half feeds the conditioner
             offset = half if self.reverse else 0               # the other half is transformed in place
-            z = self.network(cond)
+            z = self._conditioner(cond)
             out, ldj = _engine.coupling(x, z, w, None, half, offset, self.affine, direction, hw)
         else:
-            z = self.network(self.mask * x)
+            z = self._conditioner(self.mask * x)
             out, ldj = _engine.coupling(x, z, w, self._inv_mask_flat, self.in_channels * hw, 0, self.affine, direction, hw)
         return out, (ldj if self.affine else 0.0)
 

@@ -3,7 +3,6 @@ from typing import Optional, Tuple
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from ...torch.base import DensityEstimator
@@ -64,6 +63,24 @@ class RealNVP2d(NormalizingFlow):
         order = np.array([4 * c + j for j in range(4) for c in range(channels)])
         return torch.tensor(weights[order], dtype=torch.float32)
 
+    # The reference applies `perm_matrices` with F.conv2d / F.conv_transpose2d (realnvp.py:184,191); the weights
+    # are a fixed 0/1 permutation, so the same result is an exact strided gather / scatter (no multiplies,
+    # no TF32 rounding): out[:, j*C + c, h, w] = x[:, c, 2h + r_j, 2w + s_j] with taps (0,0),(1,1),(0,1),(1,0).
+    _TAPS = ((0, 0), (1, 1), (0, 1), (1, 0))
+
+    @classmethod
+    def downscale(cls, x: torch.Tensor) -> torch.Tensor:
+        return torch.cat([x[:, :, r::2, s::2] for r, s in cls._TAPS], dim=1)
+
+    @classmethod
+    def upscale(cls, y: torch.Tensor) -> torch.Tensor:
+        n, c4, h, w = y.shape
+        c = c4 // 4
+        x = y.new_empty(n, c, 2 * h, 2 * w)
+        for j, (r, s) in enumerate(cls._TAPS):
+            x[:, :, r::2, s::2] = y[:, j * c:(j + 1) * c]
+        return x
+
     def apply_backward(self, x):
         total, slices = 0.0, []
         last = len(self.layers) - 1
@@ -71,23 +88,21 @@ class RealNVP2d(NormalizingFlow):
             x, ildj = layer.apply_backward(x)
             total = total + ildj
             if i != last:
-                x = F.conv2d(x, self.perm_matrices[i], stride=2)     # fixed permutation (index shuffle)
-                x, z = torch.chunk(x, chunks=2, dim=1)
+                x, z = torch.chunk(self.downscale(x), chunks=2, dim=1)
                 slices.append(z)
         for i in range(last - 1, -1, -1):
-            x = F.conv_transpose2d(torch.cat([x, slices[i]], dim=1), self.perm_matrices[i], stride=2)
+            x = self.upscale(torch.cat([x, slices[i]], dim=1))
         return x, total
 
     def apply_forward(self, x):
         total, slices = 0.0, []
         last = len(self.layers) - 1
         for i in range(last):
-            x = F.conv2d(x, self.perm_matrices[i], stride=2)
-            x, z = torch.chunk(x, chunks=2, dim=1)
+            x, z = torch.chunk(self.downscale(x), chunks=2, dim=1)
             slices.append(z)
         for i in range(last, -1, -1):
             if i != last:
-                x = F.conv_transpose2d(torch.cat([x, slices[i]], dim=1), self.perm_matrices[i], stride=2)
+                x = self.upscale(torch.cat([x, slices[i]], dim=1))
             x, ldj = self.layers[i].apply_forward(x)
             total = total + ldj
         return x, total

@@ -75,3 +75,8 @@ def test_helpers_host():
     assert squeeze_depth2d(img).shape == (2, 12, 4, 4)
     perm = RealNVP2d.build_permutation_matrix(3)
     assert perm.shape == (12, 3, 2, 2) and float(perm.sum()) == 12.0
+    # the index form of the multi-scale permutation equals the reference's conv / conv_transpose with those weights
+    down = torch.nn.functional.conv2d(img, perm, stride=2)
+    assert torch.equal(RealNVP2d.downscale(img), down)
+    assert torch.equal(RealNVP2d.upscale(down), torch.nn.functional.conv_transpose2d(down, perm, stride=2))
+    assert torch.equal(RealNVP2d.upscale(down), img)
