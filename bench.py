@@ -248,7 +248,10 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": int(sum(launches.values())),
         "roofline": {"bound": "hbm", "kernel": "ratspn_leaf_kernel",
                      "achieved": ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                     "frac": ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9 / hbm_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65536 from the ncu --set full
+                     # capture summarised in profiles/leaf_r1.txt (x read once: 208.8 MB; leaf activations: 281.9 MB)
+                     "traffic": 490.8e6 if B == 65536 else None,
                      "peak_source": peak_src, "kernel_ms": leaf_ms,
                      "note": "path is FP32-ALU bound (220 flop/B, SURVEY.md 8d): see roofline_fp32"},
         "roofline_fp32": {"kernel": "ratspn_leaf_kernel", "achieved_tflops": 2 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12,
