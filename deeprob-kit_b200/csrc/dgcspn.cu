@@ -10,6 +10,8 @@
 // per-pixel mixture in the linear domain (one exp per input, max-shifted, exact log-domain fallback).
 // Lanes run along the contiguous H*W axis, so every access of x / W / out is coalesced, and the
 // per-pixel mixture weights are read once per CTA and reused over a slice of the batch.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -22,20 +24,23 @@ namespace dpk {
 __global__ void dgc_leaf_fwd_kernel(const float* __restrict__ x, const float* __restrict__ loc,
                                     const float* __restrict__ scale, float* __restrict__ out, int64_t B, int Cin, int K,
                                     int HW) {
-  const int64_t total = B * K * HW;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int hw = (int)(idx % HW);
-    const int k = (int)((idx / HW) % K);
-    const int64_t b = idx / ((int64_t)HW * K);
-    float acc = 0.f;
-    for (int c = 0; c < Cin; ++c) {
-      const float xv = x[(b * Cin + c) * HW + hw];
-      const size_t pi = ((size_t)k * Cin + c) * HW + hw;
-      const float sg = __ldg(scale + pi), mu = __ldg(loc + pi);
-      const float t = (xv - mu) / sg;
-      acc += nan_to_num(-0.5f * t * t - logf(sg) - kLogSqrt2Pi);
+  // blockIdx.x = (b, k) plane; threads sweep the pixels (no per-element 64-bit div/mod)
+  for (int64_t plane = blockIdx.x; plane < B * K; plane += gridDim.x) {
+    const int k = (int)(plane % K);
+    const int64_t b = plane / K;
+    const float* xb = x + b * Cin * HW;
+    float* ob = out + plane * HW;
+    for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) {
+      float acc = 0.f;
+      for (int c = 0; c < Cin; ++c) {
+        const float xv = xb[c * HW + hw];
+        const int pi = (k * Cin + c) * HW + hw;
+        const float sg = __ldg(scale + pi), mu = __ldg(loc + pi);
+        const float t = (xv - mu) / sg;
+        acc += nan_to_num(-0.5f * t * t - logf(sg) - kLogSqrt2Pi);
+      }
+      ob[hw] = acc;
     }
-    out[idx] = acc;
   }
 }
 
@@ -43,21 +48,22 @@ __global__ void dgc_leaf_fwd_kernel(const float* __restrict__ x, const float* __
 __global__ void dgc_leaf_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ loc,
                                       const float* __restrict__ scale, const float* __restrict__ g,
                                       float* __restrict__ gx, int64_t B, int Cin, int K, int HW) {
-  const int64_t total = B * Cin * HW;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int hw = (int)(idx % HW);
-    const int c = (int)((idx / HW) % Cin);
-    const int64_t b = idx / ((int64_t)HW * Cin);
-    const float xv = x[idx];
-    float acc = 0.f;
-    if (fabsf(xv) <= FLT_MAX) {
-      for (int k = 0; k < K; ++k) {
-        const size_t pi = ((size_t)k * Cin + c) * HW + hw;
-        const float sg = __ldg(scale + pi), mu = __ldg(loc + pi);
-        acc -= g[(b * K + k) * HW + hw] * (xv - mu) / (sg * sg);
+  for (int64_t plane = blockIdx.x; plane < B * Cin; plane += gridDim.x) {
+    const int c = (int)(plane % Cin);
+    const int64_t b = plane / Cin;
+    const float* gb = g + b * K * HW;
+    for (int hw = threadIdx.x; hw < HW; hw += blockDim.x) {
+      const float xv = x[plane * HW + hw];
+      float acc = 0.f;
+      if (fabsf(xv) <= FLT_MAX) {
+        for (int k = 0; k < K; ++k) {
+          const int pi = (k * Cin + c) * HW + hw;
+          const float sg = __ldg(scale + pi), mu = __ldg(loc + pi);
+          acc -= gb[k * HW + hw] * (xv - mu) / (sg * sg);
+        }
       }
+      gx[plane * HW + hw] = acc;
     }
-    gx[idx] = acc;
   }
 }
 
@@ -104,58 +110,69 @@ __device__ __forceinline__ int prod_in_channel(const ProdDesc& d, int oc, int ta
 }
 
 __global__ void dgc_product_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t B, ProdDesc d) {
-  const int64_t total = B * d.OC * d.OH * d.OW;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int ow = (int)(idx % d.OW);
-    const int oh = (int)((idx / d.OW) % d.OH);
-    const int oc = (int)((idx / ((int64_t)d.OW * d.OH)) % d.OC);
-    const int64_t b = idx / ((int64_t)d.OW * d.OH * d.OC);
-    float acc = 0.f;
+  // blockIdx.x = (b, oc) output plane; threads sweep its pixels
+  const int OHW = d.OH * d.OW;
+  for (int64_t plane = blockIdx.x; plane < B * d.OC; plane += gridDim.x) {
+    const int oc = (int)(plane % d.OC);
+    const int64_t b = plane / d.OC;
+    const float* src[4];
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
-      const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top;
-      const int xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
-      if (y >= 0 && y < d.H && xx >= 0 && xx < d.W)
-        acc += x[((b * d.C + prod_in_channel(d, oc, tap)) * d.H + y) * d.W + xx];
+    for (int tap = 0; tap < 4; ++tap) src[tap] = x + (b * d.C + prod_in_channel(d, oc, tap)) * d.H * d.W;
+    float* ob = out + plane * OHW;
+    for (int p = threadIdx.x; p < OHW; p += blockDim.x) {
+      const int oh = p / d.OW, ow = p - oh * d.OW;
+      float acc = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) {
+        const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top;
+        const int xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
+        if (y >= 0 && y < d.H && xx >= 0 && xx < d.W) acc += src[tap][y * d.W + xx];
+      }
+      ob[p] = acc;
     }
-    out[idx] = acc;
   }
 }
 
-// depthwise: gather form (thread = input element); otherwise scatter with atomics (thread = output element)
+// depthwise: gather form (CTA = input plane); otherwise scatter with atomics (CTA = output plane)
 __global__ void dgc_product_bwd_depthwise_kernel(const float* __restrict__ g, float* __restrict__ gx, int64_t B, ProdDesc d) {
-  const int64_t total = B * d.C * d.H * d.W;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int xx = (int)(idx % d.W);
-    const int y = (int)((idx / d.W) % d.H);
-    const int64_t bc = idx / ((int64_t)d.W * d.H);
-    float acc = 0.f;
+  const int HWi = d.H * d.W, OHW = d.OH * d.OW;
+  for (int64_t plane = blockIdx.x; plane < B * d.C; plane += gridDim.x) {
+    const float* gp = g + plane * OHW;
+    float* op = gx + plane * HWi;
+    for (int p = threadIdx.x; p < HWi; p += blockDim.x) {
+      const int y = p / d.W, xx = p - y * d.W;
+      float acc = 0.f;
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
-      const int ny = y + d.pad_top - (tap >> 1) * d.dh, nx = xx + d.pad_left - (tap & 1) * d.dw;
-      if (ny < 0 || nx < 0 || ny % d.sh || nx % d.sw) continue;
-      const int oh = ny / d.sh, ow = nx / d.sw;
-      if (oh < d.OH && ow < d.OW) acc += g[(bc * d.OH + oh) * d.OW + ow];
+      for (int tap = 0; tap < 4; ++tap) {
+        const int ny = y + d.pad_top - (tap >> 1) * d.dh, nx = xx + d.pad_left - (tap & 1) * d.dw;
+        if (ny < 0 || nx < 0 || ny % d.sh || nx % d.sw) continue;
+        const int oh = ny / d.sh, ow = nx / d.sw;
+        if (oh < d.OH && ow < d.OW) acc += gp[oh * d.OW + ow];
+      }
+      op[p] = acc;
     }
-    gx[idx] = acc;
   }
 }
 
 __global__ void dgc_product_bwd_scatter_kernel(const float* __restrict__ g, float* __restrict__ gx, int64_t B, ProdDesc d) {
-  const int64_t total = B * d.OC * d.OH * d.OW;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const float gv = g[idx];
-    if (gv == 0.f) continue;
-    const int ow = (int)(idx % d.OW);
-    const int oh = (int)((idx / d.OW) % d.OH);
-    const int oc = (int)((idx / ((int64_t)d.OW * d.OH)) % d.OC);
-    const int64_t b = idx / ((int64_t)d.OW * d.OH * d.OC);
+  const int OHW = d.OH * d.OW;
+  for (int64_t plane = blockIdx.x; plane < B * d.OC; plane += gridDim.x) {
+    const int oc = (int)(plane % d.OC);
+    const int64_t b = plane / d.OC;
+    const float* gp = g + plane * OHW;
+    float* dst[4];
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
-      const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top;
-      const int xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
-      if (y >= 0 && y < d.H && xx >= 0 && xx < d.W)
-        atomicAdd(gx + ((b * d.C + prod_in_channel(d, oc, tap)) * d.H + y) * d.W + xx, gv);
+    for (int tap = 0; tap < 4; ++tap) dst[tap] = gx + (b * d.C + prod_in_channel(d, oc, tap)) * d.H * d.W;
+    for (int p = threadIdx.x; p < OHW; p += blockDim.x) {
+      const float gv = gp[p];
+      if (gv == 0.f) continue;
+      const int oh = p / d.OW, ow = p - oh * d.OW;
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) {
+        const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top;
+        const int xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
+        if (y >= 0 && y < d.H && xx >= 0 && xx < d.W) atomicAdd(dst[tap] + y * d.W + xx, gv);
+      }
     }
   }
 }
@@ -228,6 +245,92 @@ __global__ void __launch_bounds__(128) dgc_sum_fwd_kernel(const float* __restric
           if (o0 + o >= O) continue;
           float y;
           if (acc[s][o] >= 1e-18f && acc[s][o] <= FLT_MAX && fabsf(m[s]) <= FLT_MAX) {
+            y = m[s] + __logf(acc[s][o]);
+          } else {  // exact log-domain evaluation
+            float mm = -INFINITY;
+            for (int i = 0; i < I; ++i)
+              mm = fmaxf(mm, x[((bb + s) * I + i) * HW + hw] + wlog[((size_t)(o0 + o) * I + i) * HW + hw]);
+            if (!(fabsf(mm) <= FLT_MAX)) {
+              y = mm;
+            } else {
+              float ss = 0.f;
+              for (int i = 0; i < I; ++i)
+                ss += expf(x[((bb + s) * I + i) * HW + hw] + wlog[((size_t)(o0 + o) * I + i) * HW + hw] - mm);
+              y = mm + logf(ss);
+            }
+          }
+          out[((bb + s) * O + o0 + o) * HW + hw] = y;
+        }
+      }
+    }
+  }
+}
+
+// Fast path when the (I x OC) weight block of a 128-pixel tile fits shared memory: the weights are staged
+// ONCE per CTA as [i][o][pixel] (each lane reads its own column: conflict-free) and reused over the whole batch
+// slice; a thread carries NB = 8 samples x OC outputs in registers, so every weight load feeds 8 FMAs.
+constexpr int kSumFastNB = 8;
+template <int OC>
+__global__ void __launch_bounds__(128) dgc_sum_fwd_smem_kernel(const float* __restrict__ x, const float* __restrict__ wsoft,
+                                                               const float* __restrict__ wlog, float* __restrict__ out,
+                                                               int64_t B, int I, int O, int HW, int64_t per_slice) {
+  extern __shared__ float wsm[];  // [I][OC][128]
+  const int lane_px = threadIdx.x;
+  const int hw = blockIdx.x * 128 + lane_px;
+  const bool live = hw < HW;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  for (int o0 = 0; o0 < O; o0 += OC) {
+    __syncthreads();
+    for (int i = 0; i < I; ++i)
+#pragma unroll
+      for (int o = 0; o < OC; ++o)
+        wsm[(i * OC + o) * 128 + lane_px] = (live && o0 + o < O) ? __ldg(wsoft + ((size_t)(o0 + o) * I + i) * HW + hw) : 0.f;
+    __syncthreads();
+    if (!live) continue;
+    for (int64_t bb = b0; bb < b1; bb += kSumFastNB) {
+      float m[kSumFastNB], acc[kSumFastNB][OC];
+      const float* xrow[kSumFastNB];   // rows past the slice are clamped: loads stay unconditional (8 in flight)
+#pragma unroll
+      for (int s = 0; s < kSumFastNB; ++s) {
+        xrow[s] = x + (size_t)min((long long)(bb + s), (long long)(b1 - 1)) * I * HW + hw;
+        m[s] = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) acc[s][o] = 0.f;
+      }
+      // pass 1: per-sample max over the inputs (they stay hot in L1/L2 for pass 2)
+#pragma unroll 2
+      for (int i = 0; i < I; ++i) {
+        float xv[kSumFastNB];
+#pragma unroll
+        for (int s = 0; s < kSumFastNB; ++s) xv[s] = xrow[s][(size_t)i * HW];
+#pragma unroll
+        for (int s = 0; s < kSumFastNB; ++s) m[s] = fmaxf(m[s], xv[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < kSumFastNB; ++s)
+        if (!(fabsf(m[s]) <= FLT_MAX)) m[s] = 0.f;     // all -inf / non-finite: the exact path sorts it out
+#pragma unroll 2
+      for (int i = 0; i < I; ++i) {
+        float w[OC], xv[kSumFastNB];
+#pragma unroll
+        for (int s = 0; s < kSumFastNB; ++s) xv[s] = xrow[s][(size_t)i * HW];
+#pragma unroll
+        for (int o = 0; o < OC; ++o) w[o] = wsm[(i * OC + o) * 128 + lane_px];
+#pragma unroll
+        for (int s = 0; s < kSumFastNB; ++s) {
+          const float e = __expf(xv[s] - m[s]);
+#pragma unroll
+          for (int o = 0; o < OC; ++o) acc[s][o] = fmaf(w[o], e, acc[s][o]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < kSumFastNB; ++s) {
+        if (bb + s >= b1) continue;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+          if (o0 + o >= O) continue;
+          float y;
+          if (acc[s][o] >= 1e-18f && acc[s][o] <= FLT_MAX) {
             y = m[s] + __logf(acc[s][o]);
           } else {  // exact log-domain evaluation
             float mm = -INFINITY;
@@ -422,6 +525,10 @@ __global__ void dgc_root_finalize_kernel(const float* __restrict__ wlog, const f
     gw[(size_t)c * Q + q] += nstat[(size_t)c * Q + q] - expf(wlog[(size_t)c * Q + q]) * s;
 }
 
+static int env_int_dgc(const char* n, int d) { const char* v = getenv(n); return (v && *v) ? atoi(v) : d; }
+
+static int plane_grid(int64_t planes) { return (int)std::min<int64_t>(planes, (int64_t)sm_count() * 64); }
+
 static int grid_for(int64_t total, int threads) {
   return (int)std::min<int64_t>(ceil_div(total, threads), (int64_t)sm_count() * 32);
 }
@@ -452,7 +559,7 @@ extern "C" int dpk_dgc_leaf_forward(const float* x, const float* loc, const floa
   if (!x || !loc || !scale || !out) return set_error(DPK_E_ARG, "dgc_leaf: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(CAT_DGC, st);
-  dgc_leaf_fwd_kernel<<<grid_for(batch * out_channels * hw, 256), 256, 0, st>>>(x, loc, scale, out, batch, in_channels,
+  dgc_leaf_fwd_kernel<<<plane_grid(batch * out_channels), 256, 0, st>>>(x, loc, scale, out, batch, in_channels,
                                                                                  out_channels, hw);
   DPK_LAUNCH_CHECK("dgc_leaf_fwd_kernel");
   return DPK_OK;
@@ -467,7 +574,7 @@ extern "C" int dpk_dgc_leaf_backward(const float* x, const float* loc, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (grad_x) {
     ProfScope prof(CAT_DGC_BWD, st);
-    dgc_leaf_bwd_x_kernel<<<grid_for(batch * in_channels * hw, 256), 256, 0, st>>>(x, loc, scale, grad_out, grad_x, batch,
+    dgc_leaf_bwd_x_kernel<<<plane_grid(batch * in_channels), 256, 0, st>>>(x, loc, scale, grad_out, grad_x, batch,
                                                                                     in_channels, out_channels, hw);
     DPK_LAUNCH_CHECK("dgc_leaf_bwd_x_kernel");
   }
@@ -493,7 +600,7 @@ extern "C" int dpk_dgc_product_forward(const dpk_dgc_product_desc* desc, const f
     return set_error(DPK_E_ARG, "dgc_product: bad descriptor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(CAT_DGC, st);
-  dgc_product_fwd_kernel<<<grid_for(batch * d.OC * d.OH * d.OW, 256), 256, 0, st>>>(x, out, batch, d);
+  dgc_product_fwd_kernel<<<plane_grid(batch * d.OC), 256, 0, st>>>(x, out, batch, d);
   DPK_LAUNCH_CHECK("dgc_product_fwd_kernel");
   return DPK_OK;
 }
@@ -507,10 +614,10 @@ extern "C" int dpk_dgc_product_backward(const dpk_dgc_product_desc* desc, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(CAT_DGC_BWD, st, d.depthwise ? 1 : 2);
   if (d.depthwise) {
-    dgc_product_bwd_depthwise_kernel<<<grid_for(batch * d.C * d.H * d.W, 256), 256, 0, st>>>(grad_out, grad_x, batch, d);
+    dgc_product_bwd_depthwise_kernel<<<plane_grid(batch * d.C), 256, 0, st>>>(grad_out, grad_x, batch, d);
   } else {
     DPK_CUDA_TRY(cudaMemsetAsync(grad_x, 0, (size_t)batch * d.C * d.H * d.W * sizeof(float), st));
-    dgc_product_bwd_scatter_kernel<<<grid_for(batch * d.OC * d.OH * d.OW, 256), 256, 0, st>>>(grad_out, grad_x, batch, d);
+    dgc_product_bwd_scatter_kernel<<<plane_grid(batch * d.OC), 256, 0, st>>>(grad_out, grad_x, batch, d);
   }
   DPK_LAUNCH_CHECK("dgc_product_bwd_kernel");
   return DPK_OK;
@@ -529,13 +636,33 @@ extern "C" int dpk_dgc_sum_forward(const float* x, const float* weight, int64_t 
   dgc_sum_prep_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(weight, wsoft, wlog, out_channels, in_channels, hw);
   DPK_LAUNCH_CHECK("dgc_sum_prep_kernel");
   const int64_t bx = ceil_div(hw, 128);
-  const int64_t per = slice_len(batch, bx, 4 * kSumNB);
-  dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
   const Chunking oc = pick_chunk(out_channels);
-  switch (oc.chunk > 8 ? 8 : oc.chunk) {   // OC = 8 covers 10/16 in two passes without blowing up registers
-    case 2: dgc_sum_fwd_kernel<2><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
-    case 4: dgc_sum_fwd_kernel<4><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
-    default: dgc_sum_fwd_kernel<8><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
+  const int OC = oc.chunk > 8 ? 8 : oc.chunk;   // OC = 8 covers 10/16/32 in several passes without blowing up registers
+  const size_t smem = (size_t)in_channels * OC * 128 * sizeof(float);
+  if (smem <= 96 * 1024) {   // weights of a pixel tile resident in shared memory
+    const int64_t per = round_up(ceil_div(batch, std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)env_int_dgc("DPK_DGC_CTAS_PER_SM", 8) * sm_count(), bx)),
+                                                                     std::max<int64_t>(1, batch / 64))), kSumFastNB);
+    dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
+#define DPK_SUM_FAST(oc_)                                                                                           \
+  {                                                                                                                 \
+    auto kern = dgc_sum_fwd_smem_kernel<oc_>;                                                                       \
+    if (smem > 48 * 1024) DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, 128, smem, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per);                  \
+  }
+    switch (OC) {
+      case 2: DPK_SUM_FAST(2) break;
+      case 4: DPK_SUM_FAST(4) break;
+      default: DPK_SUM_FAST(8) break;
+    }
+#undef DPK_SUM_FAST
+  } else {
+    const int64_t per = slice_len(batch, bx, 4 * kSumNB);
+    dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
+    switch (OC) {
+      case 2: dgc_sum_fwd_kernel<2><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
+      case 4: dgc_sum_fwd_kernel<4><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
+      default: dgc_sum_fwd_kernel<8><<<grid, 128, 0, st>>>(x, wsoft, wlog, out, batch, in_channels, out_channels, hw, per); break;
+    }
   }
   DPK_LAUNCH_CHECK("dgc_sum_fwd_kernel");
   return DPK_OK;

@@ -398,7 +398,11 @@ struct LeafLaunch {
 template <int KC, int KIND>
 static int launch_leaf_k(const LeafArgs& a, const LeafLaunch& L, cudaStream_t st) {
   ProfScope prof(CAT_LEAF, st);
-  if (L.mode == 2) {
+  if (L.mode == 4) {
+    auto kern = ratspn_leaf_kernel<KC, 4, KIND>;
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    kern<<<L.grid, 256, L.smem, st>>>(a);
+  } else if (L.mode == 2) {
     auto kern = ratspn_leaf_kernel<KC, 2, KIND>;
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kern<<<L.grid, 256, L.smem, st>>>(a);

@@ -27,7 +27,7 @@ struct RatPlan {
   Chunking kc, oc, cc;
   int np;    // table values per channel on the fast path
   // leaf kernel geometry (decided here because it fixes the table layout the prep kernel writes)
-  int leaf_mode;          // 2: 64-sample tile, 1: 32-sample tile, 0: wide fallback (no shared tile)
+  int leaf_mode;          // 4: 128-sample tile, 2: 64-sample tile, 1: 32-sample tile, 0: wide fallback (no shared tile)
   int leaf_tb;            // samples per tile
   int leaf_npk;           // floats per table row = round_up(np * KC, 4)
   int leaf_ch;            // table rows per ring chunk (<= 32)
@@ -94,9 +94,11 @@ static inline void plan_leaf_geometry(RatPlan* p) {
     }
     return 0;
   };
-  int st64 = 0, st32 = 0;
-  const int ch64 = choose(64, &st64), ch32 = choose(32, &st32);
-  if (ch64 > 0 && ceil_div(p->B, 64) >= nsm) { p->leaf_mode = 2; p->leaf_tb = 64; p->leaf_ch = ch64; p->leaf_stages = st64; }
+  int st64 = 0, st32 = 0, st128 = 0;
+  const int ch64 = choose(64, &st64), ch32 = choose(32, &st32), ch128 = choose(128, &st128);
+  if (ch128 > 0 && ceil_div(p->B, 128) >= nsm && env_int("DPK_LEAF_NO128", 0) == 0) {
+    p->leaf_mode = 4; p->leaf_tb = 128; p->leaf_ch = ch128; p->leaf_stages = st128;
+  } else if (ch64 > 0 && ceil_div(p->B, 64) >= nsm) { p->leaf_mode = 2; p->leaf_tb = 64; p->leaf_ch = ch64; p->leaf_stages = st64; }
   else if (ch32 > 0) { p->leaf_mode = 1; p->leaf_tb = 32; p->leaf_ch = ch32; p->leaf_stages = st32; }
   else { p->leaf_mode = 0; p->leaf_tb = 32; p->leaf_ch = p->dim < 16 ? p->dim : 16; p->leaf_stages = 2; }
   p->leaf_nch = (int)ceil_div(p->dim, p->leaf_ch);
