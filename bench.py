@@ -33,6 +33,7 @@ UNIT = "evals/s"
 WORKLOAD = "GaussianRatSpn(784, rg_depth=3, rg_repetitions=16, rg_batch=10, rg_sum=10) log_prob, batch 65536/GPU"
 ALGO_BYTES_PER_SAMPLE = 4 * D + 4 * C          # x row read + LL written
 ALGO_FMA_PER_SAMPLE = 348480                    # one FMA per model parameter
+LEAF_MMA_TRAFFIC = None                         # DRAM bytes per launch of the tcgen05 leaf kernel (ncu), filled in from profiles/
 
 
 def parse():
@@ -228,16 +229,23 @@ def run_b200(args, rank, local_rank, world):
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     ms_step = elapsed_ms / args.steps
     value = world * B * D / (ms_step * 1e-3)
-    leaf_ms = prof_ms["ratspn_leaf"] / max(1, launches["ratspn_leaf"])
     cats = {k: round(v / args.steps, 4) for k, v in prof_ms.items() if v > 0}
     clk = sampler.summary()
     sm_mhz = clk.get("sm_mhz") or 1965.0
     fp32_peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    leaf_fma = 2 * D * K * REPS
+    bf16_peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    leaf_fma = D * K * REPS                       # x*mu products (the unit-scale expansion; x^2 term is D*REPS more)
+    mma = launches.get("ratspn_leaf_mma", 0) > 0
+    leaf_cat = "ratspn_leaf_mma" if mma else "ratspn_leaf"
+    leaf_ms = prof_ms[leaf_cat] / args.steps
+    # dominant kernel = the leaf level (one launch per step).  Algorithmic bytes per launch: every sample's
+    # row read once + its LL written once, B samples per launch.
+    algo_gbs = ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,1), random-init parameters",
+        "vs_baseline": None, "dtype": "f32 (leaf products as 3-pass hi/lo fp16 on tcgen05, fp32 accumulate)" if mma else "f32",
+        "data": "synthetic N(0,1), random-init parameters",
         "config": {"workload": WORKLOAD, "samples_per_s": value / D, "batch_per_gpu": B,
                    "l2": "input batch 205 MB > 126 MB L2, re-read from HBM every step",
                    "parallelism": "batch-sharded x%d, all-reduce of sum(LL)" % world if world > 1 else "single GPU"},
@@ -246,20 +254,28 @@ def run_b200(args, rank, local_rank, world):
                 "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * C * 4,
                 "api": "deeprob_kit_b200.spn.streaming.log_prob_host (pinned host in/out, 2-stream chunk pipeline)"},
         "gpu_launches": int(sum(launches.values())),
-        "roofline": {"bound": "hbm", "kernel": "ratspn_leaf_kernel",
-                     "achieved": ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9 / hbm_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65536 from the ncu --set full
-                     # capture summarised in profiles/leaf_r1.txt (x read once: 208.8 MB; leaf activations: 281.9 MB)
-                     "traffic": 490.8e6 if B == 65536 else None,
+        "roofline": {"bound": "hbm", "kernel": "ratspn_leaf_mma_kernel" if mma else "ratspn_leaf_kernel",
+                     "achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65536 (ncu --set full,
+                     # profiles/leaf_mma_r1.txt resp. profiles/leaf_r1.txt): x read once + the leaf activations written
+                     "traffic": (LEAF_MMA_TRAFFIC if mma else 490.8e6) if B == 65536 else None,
                      "peak_source": peak_src, "kernel_ms": leaf_ms,
-                     "note": "path is FP32-ALU bound (220 flop/B, SURVEY.md 8d): see roofline_fp32"},
-        "roofline_fp32": {"kernel": "ratspn_leaf_kernel", "achieved_tflops": 2 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12,
-                          "peak_tflops_at_observed_clock": fp32_peak_tf,
-                          "frac": 2 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12 / fp32_peak_tf,
-                          "whole_step_tflops": 2 * ALGO_FMA_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12},
+                     "note": "the path is compute bound (220 flop/B, SURVEY.md 8d): see roofline_tensor / roofline_fp32"},
         "kernel_ms_per_step": cats,
     }
+    if mma:
+        # dense tensor-core work actually issued: 3 passes x (B x 784 x 1280) + 2 passes x (B x 784 x 128)
+        dense = 2.0 * B * D * (3 * REPS * (1 << DEPTH) * K + 2 * REPS * (1 << DEPTH))
+        line["roofline_tensor"] = {"kernel": "ratspn_leaf_mma_kernel", "issued_tflops": dense / (leaf_ms * 1e-3) / 1e12,
+                                   "peak_tflops": bf16_peak_tf, "frac": dense / (leaf_ms * 1e-3) / 1e12 / bf16_peak_tf,
+                                   "useful_tflops": 2.0 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12,
+                                   "note": "issued = dense fp16 MMA flops incl. the zero blocks of the region structure and "
+                                           "the 3-pass split; peak = measured cuBLAS bf16 (sustained)"}
+    else:
+        line["roofline_fp32"] = {"kernel": "ratspn_leaf_kernel", "achieved_tflops": 4 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12,
+                                 "peak_tflops_at_observed_clock": fp32_peak_tf,
+                                 "frac": 4 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12 / fp32_peak_tf}
+    line["whole_step_tflops_fp32_equiv"] = 2 * ALGO_FMA_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12
     if world == 1 and not args.no_cpu_baseline:
         v, _, cores, sample = time_oracle(8, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

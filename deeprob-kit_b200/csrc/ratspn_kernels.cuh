@@ -7,6 +7,9 @@ namespace dpk {
 int ratspn_check_ws(const RatPlan& p, const void* ws, size_t bytes);
 // leaf tables (tab / cd / cst) from the leaf parameters           [ratspn_leaf.cu]
 int ratspn_run_prep_leaf(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
+// tensor-core leaf: weight images / constants, and x -> act[0] for every clean 32-sample group (flags the rest)
+int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
+int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_t st);
 // softmax / log-softmax tables of every sum level and of the root [ratspn_einsum.cu]
 int ratspn_run_prep_weights(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
 // x -> act[0]                                                      [ratspn_leaf.cu]

@@ -95,6 +95,7 @@ struct LeafArgs {
   const float* cd;           // [G0][nKc][dim][KC]
   const float* cst;          // [G0][Kp]
   float* out;                // [G0][K][Bp]
+  const int* redo;           // NULL, or [Bp/32]: only tiles with a flagged 32-sample group are computed
   int64_t B, Bp;
   int D, G0, K, dim, nKc, regions_per_cta;
   LeafTabGeom g;
@@ -165,6 +166,12 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * TB;
   const int CH = a.g.CH, NCH = a.g.NCH, CHP = a.g.CHP, CF = a.g.CF, NST = a.g.NST;
+  if (a.redo) {   // clean-up pass behind the tensor-core kernel: most tiles have nothing to redo
+    int any = 0;
+#pragma unroll
+    for (int s = 0; s < ST; ++s) any |= __ldg(a.redo + (b0 >> 5) + s);
+    if (!any) return;
+  }
 
   float* xs = reinterpret_cast<float*>(smem_raw);
   float* ring = xs + (size_t)a.D * TB + (size_t)warp * NST * CF;
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
   uint32_t c_parity = 0;
   for (int ri = 0; ri < n_reg; ++ri) {
     const int r = r_begin + warp + 8 * ri;
+    const int len_r = __ldg(a.region_len + r);   // pad slots (d >= len_r) are not swept: they contribute exactly 0
     for (int c = 0; c < a.nKc; ++c) {
       float2 acc[ST][KH];
 #pragma unroll
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
         const float* __restrict__ chunk = ring + (size_t)c_stage * CF;
         const uint32_t* __restrict__ hdr = reinterpret_cast<const uint32_t*>(chunk);
         const float* __restrict__ rows = chunk + CHP;
-        const int nrows = min(CH, a.dim - ch * CH);
+        const int nrows = max(0, min(CH, len_r - ch * CH));
 
         // Software pipeline, per row d: header word fetched 2 rows ahead, x + parameters 1 row ahead,
         // so that no shared-memory latency sits between the FFMA2 blocks of consecutive rows.
@@ -337,6 +345,7 @@ __global__ void __launch_bounds__(256) ratspn_leaf_wide_kernel(const LeafArgs a)
   constexpr int NPK = (NP * KC + 3) / 4 * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * 32 + lane;
+  if (a.redo && !__ldg(a.redo + blockIdx.x)) return;
   const int r_begin = blockIdx.y * a.regions_per_cta;
   const int r_end = min(a.G0, r_begin + a.regions_per_cta);
   for (int r = r_begin + warp; r < r_end; r += 8) {
@@ -455,6 +464,7 @@ int ratspn_run_prep_leaf(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, 
   ratspn_prep_const_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws + p.off_cd, d->region_len, p.G0, p.dim, p.kc.chunk,
                                                              p.kc.count, ws + p.off_cst);
   DPK_LAUNCH_CHECK("ratspn_prep_const_kernel");
+  if (p.leaf_mma) return ratspn_run_prep_leaf_mma(d, p, ws, st);
   return DPK_OK;
 }
 
@@ -462,6 +472,14 @@ int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, 
   LeafArgs a;
   a.x = x; a.mask = d->mask; a.region_len = d->region_len;
   a.tab = ws + p.off_tab; a.cd = ws + p.off_cd; a.cst = ws + p.off_cst; a.out = ws + p.off_act[0];
+  a.redo = nullptr;
+  if (p.leaf_mma && ((uintptr_t)x & 15) == 0) {
+    // tensor-core pass first; the exact kernel below then redoes only the flagged sample groups
+    ProfScope prof(CAT_LEAF_MMA, st);
+    int rc = ratspn_run_leaf_mma(p, x, ws, st);
+    if (rc) return rc;
+    a.redo = reinterpret_cast<const int*>(ws + p.off_mflags);
+  }
   a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
   a.g = leaf_geom(p);
   const int nsm = sm_count();

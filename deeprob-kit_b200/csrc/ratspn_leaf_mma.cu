@@ -1,0 +1,526 @@
+// ratspn_leaf_mma.cu -- RAT-SPN leaf level on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// RegionGraphLayer.forward (deeprob/spn/layers/ratspn.py:87-108) with unit-scale Gaussian leaves
+// (GaussianLayer :160-213, optimize_scale=False) or Bernoulli leaves (:216-247) is linear in the
+// parameters once the square is expanded:
+//     Gaussian  sum_d -(x_d - mu_d)^2/2 - log sqrt(2 pi) = sum_d x_d mu_d  -  sum_d x_d^2 / 2  +  c
+//     Bernoulli sum_d x_d l_d - softplus(l_d)            = sum_d x_d l_d                      +  c
+// so the whole level is one GEMM  out[b, (g,k)] = sum_f x[b,f] W[f,(g,k)]  with W[f,(g,k)] = param if
+// feature f belongs to region g (else 0), plus -- for the Gaussian -- a second GEMM of x^2 against the
+// 0/1 region indicator.  x is used in its natural feature order, so nothing is gathered: the random
+// region structure lives entirely in the (sparse, L2-resident) weight images.
+//
+// fp32 accuracy on fp16 tensor cores: every operand is split v = hi + lo (two fp16, 22 significant
+// bits) and the product is taken in three passes hi*hi + lo*hi + hi*lo with fp32 accumulation in
+// TMEM (the indicator is exact, so the x^2 GEMM needs two).  Inputs outside the range where the
+// split is exact (NaN = marginalised, inf, |x| > limit) flag their 32-sample group, which the exact
+// CUDA-core kernel (ratspn_leaf.cu) then redoes; parameters outside the fp16 range flag everything.
+//
+// Kernel shape: persistent, one CTA per SM, 18 warps:
+//   warp 0      bulk-copy (TMA 1-D, UBLKCP) producer of the pre-swizzled weight images
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue
+//   warps 2-9   operand converters: coalesced 16-byte loads of x, hi/lo split, 64B-swizzled K-major stores
+//   warps 10-17 epilogue: tcgen05.ld, + per-column constant, + per-region -x^2/2, coalesced stores into
+//               the sample-minor activation layout act[0] = [G0*K][Bp]
+// Units are handed out in increasing order by an atomic counter (warp 0 publishes the unit through a small
+// shared-memory ring), M-tile-major with the x^2 units of an M tile first: CTAs that run at the same time
+// work on the same few M tiles, so x is read from HBM once and re-read from L2, and the load is balanced
+// dynamically.  W units read the x^2 sums of their M tile from a global scratch guarded by a per-M-tile
+// ready counter; the unit that produces them always has a smaller index, i.e. is already running.
+// A unit of work = (256-sample M tile, 256-column N tile): two M=128 accumulators of 256 fp32 columns
+// (all 512 TMEM columns) share every weight stage, so the 4 MB weight image is streamed once per 256
+// samples.  K is walked in 32-feature blocks through a 3-stage ring of {A hi, A lo, B hi, B lo} 16 KB
+// images synchronised with mbarriers (full: 8 converter warps + expect_tx bytes; empty: tcgen05.commit).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "ratspn_kernels.cuh"
+
+namespace dpk {
+
+namespace {
+
+constexpr int kImg = kMmaTileN * kMmaKB * 2;  // 16 KB: [256 rows][64 B] fp16, 64B-swizzled, K-major
+constexpr int kStage = 4 * kImg;              // A hi | A lo | B hi | B lo
+constexpr int kThreads = 576;
+constexpr int kEpiThread0 = 320;              // first epilogue thread (warp 10)
+constexpr uint32_t kSpinLimit = 1u << 22;     // bounded waits: a broken pipeline traps instead of hanging
+
+struct LeafMmaArgs {
+  const float* x;
+  int64_t B, Bp;
+  int D, quad, G0, K, Ntot;
+  int nS, nW, KBn, last_ks, nM;
+  const unsigned char* wimg;  // [nW][KBn][hi | lo][16 KB]
+  const unsigned char* simg;  // [nS][KBn][16 KB] region indicator (exact in fp16)
+  const float* cstm;          // [Ntot] additive constant of every column
+  float* sq;                  // [G0][Bp] scratch: -1/2 sum_{f in region} x_f^2
+  float* out;                 // [Ntot][Bp]
+  int* redo;                  // [Bp/32] groups the exact kernel must redo
+  const int* wflag;           // != 0: parameters not representable, redo everything
+  int* unit_counter;          // dynamic scheduler (zeroed before the launch)
+  int* sq_ready;              // [nM] number of finished x^2 units of every M tile (zeroed before the launch)
+  float xlimit;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 operands, fp32 accumulate, M = 128, N from the instruction descriptor
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand, 64-byte swizzle: rows 64 B apart, 8-row groups 512 B apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
+// byte offset of 16-byte chunk `c` (0..3) of row `row` inside a 64B-swizzled image
+__host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t c) {
+  return row * 64u + ((c ^ ((row >> 1) & 3u)) << 4);
+}
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units behind the scheduler (3 stages + 2)
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const LeafMmaArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;   // swizzled images need 1024-byte alignment
+  unsigned char* sm = smem_raw + (base - raw);
+  float* cst_s = reinterpret_cast<float*>(sm + kMmaStages * kStage);
+  int* gcol_s = reinterpret_cast<int*>(cst_s + kMmaTileN);
+  float* sqw_s = reinterpret_cast<float*>(gcol_s + kMmaTileN);        // [8 epilogue warps][16 regions][32 lanes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sqw_s + 8 * 16 * 32);
+  uint64_t* full = bars;                 // [stages] A converted (8 warps) + B landed (tx bytes)
+  uint64_t* empty = bars + kMmaStages;   // [stages] MMAs that read the stage have completed
+  uint64_t* tfull = bars + 2 * kMmaStages;   // accumulators of the unit complete
+  uint64_t* tempty = tfull + 1;              // epilogue drained the accumulators
+  uint64_t* sfull = tempty + 1;              // [kSchedSlots] unit index published
+  int* sched_s = reinterpret_cast<int*>(sfull + kSchedSlots);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_s + kSchedSlots);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (__ldg(a.wflag) != 0) {  // parameters outside the fp16 range: the exact kernel does everything
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.Bp / 32; i += (int64_t)gridDim.x * blockDim.x)
+      a.redo[i] = 1;
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMmaStages; ++s) { mbar_init(full + s, 9); mbar_init(empty + s, 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 8);
+    for (int s = 0; s < kSchedSlots; ++s) mbar_init(sfull + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int upm = a.nS + a.nW;
+  const int n_units = a.nM * upm;
+  // every role walks the same unit sequence: entry `it` of the scheduler ring
+  auto next_unit = [&](int it, int* m, int* j) -> bool {
+    mbar_wait(sfull + (it & (kSchedSlots - 1)), (uint32_t)(it / kSchedSlots) & 1u);
+    const int u = sched_s[it & (kSchedSlots - 1)];
+    if (u < 0) return false;
+    *m = u / upm; *j = u - *m * upm;
+    return true;
+  };
+  int m, j;
+
+  if (warp == 0) {
+    // ---------------- scheduler + weight-image producer ----------------
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0;; ++it) {
+      int u = 0;
+      if (lane == 0) {
+        u = atomicAdd(a.unit_counter, 1);
+        if (u >= n_units) u = -1;
+        sched_s[it & (kSchedSlots - 1)] = u;
+        mbar_arrive(sfull + (it & (kSchedSlots - 1)));   // release: the store above is visible to the waiters
+      }
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u < 0) break;
+      m = u / upm; j = u - m * upm;
+      const bool isS = j < a.nS;
+      const unsigned char* src = isS ? a.simg + (size_t)j * a.KBn * kImg : a.wimg + (size_t)(j - a.nS) * a.KBn * (2 * kImg);
+      const uint32_t bytes = isS ? kImg : 2 * kImg;
+      for (int kb = 0; kb < a.KBn; ++kb) {
+        if (lane == 0) {
+          mbar_wait(empty + stage, phase ^ 1u);
+          mbar_expect_tx(full + stage, bytes);
+          bulk_g2s(base + stage * kStage + 2 * kImg, src + (size_t)kb * bytes, bytes, full + stage);
+        }
+        __syncwarp();
+        if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issue (one thread) ----------------
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; next_unit(it, &m, &j); ++it) {
+      const bool isS = j < a.nS;
+      const int cols = isS ? a.G0 - j * kMmaTileN : a.Ntot - (j - a.nS) * kMmaTileN;
+      const int N = min(kMmaTileN, (cols + 15) / 16 * 16);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);  // fp32 accum, fp16 A/B, K-major, M=128
+      if (lane == 0) {
+        if (it > 0) mbar_wait(tempty, (uint32_t)(it - 1) & 1u);
+        tc_fence_after();
+      }
+      for (int kb = 0; kb < a.KBn; ++kb) {
+        if (lane == 0) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * kStage;
+          const int nks = (kb == a.KBn - 1) ? a.last_ks : 2;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t b_hi = smem_desc_sw64(sa + 2 * kImg + ks * 32);
+            const uint64_t b_lo = smem_desc_sw64(sa + 3 * kImg + ks * 32);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint64_t a_hi = smem_desc_sw64(sa + h * (kImg / 2) + ks * 32);
+              const uint64_t a_lo = smem_desc_sw64(sa + kImg + h * (kImg / 2) + ks * 32);
+              const uint32_t d = tmem + h * kMmaTileN;
+              tc_mma(d, a_hi, b_hi, idesc, (kb | ks) != 0);
+              tc_mma(d, a_lo, b_hi, idesc, 1u);
+              if (!isS) tc_mma(d, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          tc_commit(empty + stage);
+          if (kb == a.KBn - 1) tc_commit(tfull);
+        }
+        __syncwarp();
+        if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp < 10) {
+    // ---------------- operand converters ----------------
+    const int cw = warp - 2;
+    const int c8 = lane & 7, rsub = lane >> 3;
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; next_unit(it, &m, &j); ++it) {
+      const bool isS = j < a.nS;
+      const bool check = (j == 0);
+      const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
+      auto load = [&](int kb, float4 (&v)[8]) {
+        const int f0 = kb * kMmaKB + c8 * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t b = b0 + 4 * i;
+          v[i] = (b < a.B && f0 < a.D) ? ldg_stream(a.x + b * a.D + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto convert = [&](float4 (&buf)[8]) {
+        mbar_wait(empty + stage, phase ^ 1u);
+        unsigned char* A = sm + stage * kStage;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 v = buf[i];
+          if (check) {
+            const bool bad = !(fabsf(v.x) <= a.xlimit) || !(fabsf(v.y) <= a.xlimit) || !(fabsf(v.z) <= a.xlimit) ||
+                             !(fabsf(v.w) <= a.xlimit);
+            if (bad) a.redo[(b0 + 4 * i) >> 5] = 1;
+          }
+          if (isS) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
+          const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+          const uint32_t row = cw * 32 + 4 * i + rsub;
+          const uint32_t off = sw64_off(row, c8 >> 1) + (c8 & 1) * 8;
+          uint2 hv, lv;
+          hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+          lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(A + off) = hv;
+          *reinterpret_cast<uint2*>(A + kImg + off) = lv;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + stage);
+        if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
+      };
+      // two register sets, loads two K blocks ahead of their use (no register copies: a copy would wait for the load)
+      float4 bufA[8], bufB[8];
+      load(0, bufA);
+      if (a.KBn > 1) load(1, bufB);
+      for (int kb = 0; kb < a.KBn; kb += 2) {
+        convert(bufA);
+        if (kb + 2 < a.KBn) load(kb + 2, bufA);
+        if (kb + 1 < a.KBn) {
+          convert(bufB);
+          if (kb + 3 < a.KBn) load(kb + 3, bufB);
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int et = threadIdx.x - kEpiThread0;   // 0..255
+    const int ew = warp - 10;
+    const int q = warp & 3;                     // TMEM lane quarter this warp may read
+    const int chalf = ew >> 2;                  // which 128 columns of the tile
+    float* sqw = sqw_s + ew * (16 * 32);
+    for (int it = 0; next_unit(it, &m, &j); ++it) {
+      const bool isS = j < a.nS;
+      const int col_base = (isS ? j : j - a.nS) * kMmaTileN;
+      const int cols = (isS ? a.G0 : a.Ntot) - col_base;
+      const bool quad = !isS && a.quad;
+      if (!isS) {
+        const int n = col_base + et;
+        cst_s[et] = (n < a.Ntot) ? __ldg(a.cstm + n) : 0.f;
+        gcol_s[et] = (n < a.Ntot) ? n / a.K : a.G0 - 1;
+      }
+      epi_bar();
+      // regions covered by this warp's 128 columns; their -x^2/2 sums are staged per (half, lane) in shared memory
+      const int g_lo = quad ? gcol_s[chalf * 128] : 0;
+      float pre[16];
+      auto preload = [&](int h) {
+        const int64_t b = (int64_t)m * kMmaTileM + h * 128 + q * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+          pre[r] = (g_lo + r < a.G0 && b < a.Bp) ? __ldcg(a.sq + (size_t)(g_lo + r) * a.Bp + b) : 0.f;
+      };
+      auto stage_pre = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sqw[r * 32 + lane] = pre[r];
+        __syncwarp();
+      };
+      if (quad && chalf * 128 < cols) {
+        // the x^2 units of this M tile have smaller unit indices: they are running or done
+        for (uint32_t spin = 0; ld_acquire(a.sq_ready + m) < a.nS; ++spin) {
+          __nanosleep(64);
+          if (spin > (1u << 24)) __trap();
+        }
+        preload(0);
+      }
+      mbar_wait(tfull, (uint32_t)it & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int64_t b = (int64_t)m * kMmaTileM + h * 128 + q * 32 + lane;
+        const bool bok = b < a.Bp;
+        if (quad && chalf * 128 < cols) {
+          stage_pre();
+          if (h == 0) preload(1);
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col0 = chalf * 128 + cc * 32;
+          if (col0 >= cols) break;
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * kMmaTileN + col0);
+          uint32_t v[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (isS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int g = col_base + col0 + i;
+              if (g < a.G0 && bok) a.sq[(size_t)g * a.Bp + b] = -0.5f * __uint_as_float(v[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int n = col_base + col0 + i;
+              if (n < a.Ntot && bok) {
+                float add = cst_s[col0 + i];
+                if (quad) {
+                  const int r = gcol_s[col0 + i] - g_lo;
+                  add += (r < 16) ? sqw[r * 32 + lane] : __ldcg(a.sq + (size_t)(g_lo + r) * a.Bp + b);
+                }
+                __stcs(a.out + (size_t)n * a.Bp + b, __uint_as_float(v[i]) + add);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      if (isS) __threadfence();   // x^2 sums: visible device-wide before the ready counter moves
+      epi_bar();
+      if (isS && et == 0) atomicAdd(a.sq_ready + m, 1);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---- weight images ---------------------------------------------------------------------------------
+template <int KIND>
+__global__ void ratspn_prep_leaf_mma_kernel(const float* __restrict__ p0, const int32_t* __restrict__ mask,
+                                            const int32_t* __restrict__ region_len, int G0, int K, int dim, int KBn,
+                                            unsigned char* __restrict__ wimg, unsigned char* __restrict__ simg,
+                                            int* __restrict__ wflag) {
+  const int64_t total = (int64_t)G0 * K * dim;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % dim);
+    const int k = (int)((idx / dim) % K);
+    const int g = (int)(idx / ((int64_t)dim * K));
+    if (d >= region_len[g]) continue;          // pad slots contribute exactly 0 (ratspn.py:104-105)
+    const int f = mask[(size_t)g * dim + d];
+    const float w = p0[idx];
+    if (!(fabsf(w) <= 60000.f)) *wflag = 1;
+    const int n = g * K + k;
+    const uint32_t off = sw64_off((uint32_t)(n & (kMmaTileN - 1)), (uint32_t)(f & 31) >> 3) + (uint32_t)(f & 7) * 2u;
+    unsigned char* img = wimg + ((size_t)(n / kMmaTileN) * KBn + (f >> 5)) * (2 * kImg);
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    *reinterpret_cast<__half*>(img + off) = hi;
+    *reinterpret_cast<__half*>(img + kImg + off) = lo;
+    if (KIND == kLeafGaussUnit && k == 0) {
+      const uint32_t soff = sw64_off((uint32_t)(g & (kMmaTileN - 1)), (uint32_t)(f & 31) >> 3) + (uint32_t)(f & 7) * 2u;
+      *reinterpret_cast<__half*>(simg + ((size_t)(g / kMmaTileN) * KBn + (f >> 5)) * kImg + soff) = __float2half_rn(1.f);
+    }
+  }
+}
+
+template <int KIND>
+__global__ void ratspn_prep_leaf_mma_const_kernel(const float* __restrict__ p0, const int32_t* __restrict__ region_len,
+                                                  int G0, int K, int dim, float* __restrict__ cstm) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G0 * K) return;
+  const int g = idx / K;
+  const int len = region_len[g];
+  const float* __restrict__ p = p0 + (size_t)idx * dim;
+  float s = 0.f;
+  for (int d = 0; d < len; ++d) {
+    const float w = p[d];
+    if (KIND == kLeafGaussUnit) s += fmaf(-0.5f * w, w, -kLogSqrt2Pi);
+    else s -= fmaxf(w, 0.f) + log1pf(expf(-fabsf(w)));
+  }
+  cstm[idx] = s;
+}
+
+}  // namespace
+
+// flags block: redo[Bp/32] | wflag | unit counter | sq_ready[nM]
+static size_t mma_flag_ints(const RatPlan& p) { return (size_t)p.Bp / 32 + 2 + (size_t)ceil_div(p.B, kMmaTileM); }
+
+int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st) {
+  unsigned char* wimg = reinterpret_cast<unsigned char*>(ws + p.off_wimg);
+  unsigned char* simg = reinterpret_cast<unsigned char*>(ws + p.off_simg);
+  int* flags = reinterpret_cast<int*>(ws + p.off_mflags);
+  // images (wimg, simg are adjacent) and flags are rebuilt every call: parameters change in place
+  DPK_CUDA_TRY(cudaMemsetAsync(wimg, 0, (size_t)(p.mma_nW * 2 + p.mma_nS) * p.mma_kb * kImg, st));
+  DPK_CUDA_TRY(cudaMemsetAsync(flags, 0, mma_flag_ints(p) * 4, st));
+  const int64_t total = (int64_t)p.G0 * p.K * p.dim;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
+  int* wflag = flags + p.Bp / 32;
+  if (p.fwd_kind == kLeafGaussUnit) {
+    ratspn_prep_leaf_mma_kernel<kLeafGaussUnit><<<blocks, 256, 0, st>>>(d->leaf_p0, d->mask, d->region_len, p.G0, p.K,
+                                                                         p.dim, p.mma_kb, wimg, simg, wflag);
+    ratspn_prep_leaf_mma_const_kernel<kLeafGaussUnit><<<(p.G0 * p.K + 127) / 128, 128, 0, st>>>(
+        d->leaf_p0, d->region_len, p.G0, p.K, p.dim, ws + p.off_cstm);
+  } else {
+    ratspn_prep_leaf_mma_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(d->leaf_p0, d->mask, d->region_len, p.G0,
+                                                                             p.K, p.dim, p.mma_kb, wimg, simg, wflag);
+    ratspn_prep_leaf_mma_const_kernel<DPK_LEAF_BERNOULLI><<<(p.G0 * p.K + 127) / 128, 128, 0, st>>>(
+        d->leaf_p0, d->region_len, p.G0, p.K, p.dim, ws + p.off_cstm);
+  }
+  DPK_LAUNCH_CHECK("ratspn_prep_leaf_mma_kernel");
+  return DPK_OK;
+}
+
+int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_t st) {
+  LeafMmaArgs a;
+  a.x = x; a.B = p.B; a.Bp = p.Bp; a.D = p.D;
+  a.quad = (p.fwd_kind == kLeafGaussUnit) ? 1 : 0;
+  a.G0 = p.G0; a.K = p.K; a.Ntot = p.G0 * p.K;
+  a.nS = p.mma_nS; a.nW = p.mma_nW; a.KBn = p.mma_kb;
+  a.last_ks = ((p.D + 15) / 16) % 2 == 1 ? 1 : 2;
+  a.nM = (int)ceil_div(p.B, kMmaTileM);
+  a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_wimg);
+  a.simg = reinterpret_cast<const unsigned char*>(ws + p.off_simg);
+  a.cstm = ws + p.off_cstm;
+  a.sq = ws + p.off_sq;
+  a.out = ws + p.off_act[0];
+  a.redo = reinterpret_cast<int*>(ws + p.off_mflags);
+  a.wflag = a.redo + p.Bp / 32;
+  a.unit_counter = a.redo + p.Bp / 32 + 1;
+  a.sq_ready = a.redo + p.Bp / 32 + 2;
+  a.xlimit = a.quad ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
+  const int n_units = a.nM * (a.nS + a.nW);
+  const int grid = std::min(sm_count(), n_units);
+  const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ratspn_leaf_mma_kernel<<<grid, kThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel");
+  return DPK_OK;
+}
+
+}  // namespace dpk

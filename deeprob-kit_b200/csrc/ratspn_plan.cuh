@@ -36,6 +36,10 @@ struct RatPlan {
   int leaf_chunk_floats;  // leaf_chp + leaf_ch * leaf_npk
   int leaf_stages;        // ring depth (2..kLeafMaxStages)
   size_t leaf_smem;       // dynamic shared memory of the leaf kernel
+  // tensor-core leaf (ratspn_leaf_mma.cu): 0 = not used for this call
+  int leaf_mma;
+  int mma_nS, mma_nW, mma_kb;  // x^2 (region indicator) N tiles, weight N tiles, 32-feature K blocks
+  size_t off_wimg, off_simg, off_cstm, off_sq, off_mflags;
   int act_regions[DPK_MAX_LEVELS], act_ch[DPK_MAX_LEVELS];
   size_t off_tab, off_cd, off_cst;
   size_t off_wsoft[DPK_MAX_LEVELS], off_wlog[DPK_MAX_LEVELS], w_floats[DPK_MAX_LEVELS];
@@ -54,6 +58,9 @@ static inline size_t align64(size_t v) { return (v + 63) / 64 * 64; }
 constexpr int kLeafMaxStages = 4;  // per-warp ring depth of TMA-bulk parameter chunks (upper bound)
 constexpr int kLeafWarps = 8;
 constexpr int kLeafGaussUnit = 2;  // internal leaf flavour: Gaussian with scale == 1 (desc->leaf_p1 == NULL)
+// tensor-core leaf tiling: 256 samples x 256 columns per unit, 32 features per K block, 3-stage ring
+constexpr int kMmaTileM = 256, kMmaTileN = 256, kMmaKB = 32, kMmaStages = 3;
+constexpr int64_t kMmaMinBatch = 8192;  // below this the persistent grid cannot fill the SMs
 
 static inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -134,6 +141,28 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
   p->off_tab = take((size_t)p->G0 * p->kc.count * p->leaf_nch * p->leaf_chunk_floats);
   p->off_cd = take((size_t)p->G0 * p->kc.count * p->dim * p->kc.chunk);
   p->off_cst = take((size_t)p->G0 * p->kc.padded);
+  // Tensor-core leaf: linear-in-parameters flavours only (unit-scale Gaussian, Bernoulli), 16-byte
+  // loadable rows.  DPK_LEAF_MMA=0 disables it, =1 forces it for any batch size (tests).
+  {
+    const int knob = env_int("DPK_LEAF_MMA", -1);
+    const size_t mma_smem = (size_t)kMmaStages * 4 * kMmaTileN * kMmaKB * 2 + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+    p->leaf_mma = (p->fwd_kind != DPK_LEAF_GAUSSIAN && p->D % 4 == 0 && knob != 0 &&
+                   (batch >= kMmaMinBatch || knob == 1) && mma_smem <= (size_t)max_dynamic_smem())
+                      ? 1 : 0;
+    p->mma_nS = p->mma_nW = p->mma_kb = 0;
+    p->off_wimg = p->off_simg = p->off_cstm = p->off_sq = p->off_mflags = 0;
+    if (p->leaf_mma) {
+      p->mma_nS = (p->fwd_kind == kLeafGaussUnit) ? (int)ceil_div(p->G0, kMmaTileN) : 0;
+      p->mma_nW = (int)ceil_div((int64_t)p->G0 * p->K, kMmaTileN);
+      p->mma_kb = (int)ceil_div(p->D, kMmaKB);
+      const size_t img_floats = (size_t)kMmaTileN * kMmaKB * 2 / 4;
+      p->off_wimg = take((size_t)p->mma_nW * p->mma_kb * 2 * img_floats);
+      p->off_simg = take((size_t)p->mma_nS * p->mma_kb * img_floats);   // directly behind wimg (one memset)
+      p->off_cstm = take((size_t)p->G0 * p->K);
+      p->off_sq = take((size_t)p->G0 * p->Bp);
+      p->off_mflags = take((size_t)p->Bp / 32 + 2 + (size_t)ceil_div(p->B, kMmaTileM));
+    }
+  }
   for (int l = 0; l < p->depth; ++l) {
     p->act_regions[l] = p->G0 >> l;
     p->act_ch[l] = (l == 0) ? p->K : p->O;

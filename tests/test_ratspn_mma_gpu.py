@@ -1,0 +1,130 @@
+"""GPU parity of the tensor-core (tcgen05) leaf path, csrc/ratspn_leaf_mma.cu, against the float64 oracle.
+
+The path is selected automatically for batches >= 8192; DPK_LEAF_MMA=1 forces it for the small batches
+the oracle finishes in seconds, DPK_LEAF_MMA=0 gives the CUDA-core kernel to compare with.  Leaf values
+are held to 2e-6 relative (the hi/lo fp16 split carries 22 bits), whole-model log-likelihoods to the
+north-star 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+import param_gen as pg
+from conftest import norm_err, rel_err
+from helpers import oracle_for, product_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CASES = {
+    # north-star structure, batch not a multiple of the 256-sample tile
+    "gauss784": dict(kind="gaussian", in_features=784, rg_depth=3, rg_repetitions=16, rg_batch=10, rg_sum=10,
+                     out_classes=1, batch=700, nan_frac=0.0, optimize_scale=False),
+    # padded regions (36 / 8 = 4.5), K not a multiple of anything, > 256 columns, 2 K blocks (last one short)
+    "gauss36": dict(kind="gaussian", in_features=36, rg_depth=3, rg_repetitions=9, rg_batch=7, rg_sum=3,
+                    out_classes=2, batch=300, nan_frac=0.0, optimize_scale=False),
+    "gauss_deep": dict(pg.RATSPN_CASES["gauss_deep"], batch=513),
+    # > 256 regions: two x^2 tiles
+    "gauss_wide": dict(kind="gaussian", in_features=128, rg_depth=5, rg_repetitions=10, rg_batch=4, rg_sum=3,
+                       out_classes=1, batch=260, nan_frac=0.0, optimize_scale=False),
+    "bern784": dict(pg.RATSPN_CASES["bern784"], batch=333),
+    "bern16": dict(pg.RATSPN_CASES["bern16"], batch=257),
+    # marginalised inputs: flagged 32-sample groups are redone by the exact kernel
+    "gauss784_nan": dict(kind="gaussian", in_features=784, rg_depth=3, rg_repetitions=16, rg_batch=10, rg_sum=10,
+                         out_classes=1, batch=400, nan_frac=0.001, optimize_scale=False),
+    "bern36_nan": dict(kind="bernoulli", in_features=36, rg_depth=3, rg_repetitions=9, rg_batch=7, rg_sum=3,
+                       out_classes=2, batch=300, nan_frac=0.01, binary=True),
+}
+
+
+def _run(cfg, monkeypatch, mma):
+    monkeypatch.setenv("DPK_LEAF_MMA", "1" if mma else "0")
+    model = product_model(cfg, DEV, scale_grad=False)
+    x, g = pg.ratspn_inputs(cfg)
+    xd = x.to(DEV)
+    leaf = model.base_layer(xd).cpu()
+    out = model(xd).cpu()
+    return model, x, g, leaf, out
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_mma_leaf_matches_float64_oracle(name, monkeypatch):
+    cfg = CASES[name]
+    orc = oracle_for(cfg)[0].double()
+    _, x, _, leaf, out = _run(cfg, monkeypatch, True)
+    ref_leaf = orc.leaf(x.double())
+    ref_out = orc.log_prob(x.double())
+    assert leaf.shape == ref_leaf.shape
+    assert rel_err(leaf, ref_leaf) < 2e-6, "leaf"
+    assert rel_err(out, ref_out) < 1e-4, "log_prob"
+    # the CUDA-core kernel on the same inputs: both paths agree to fp32 rounding
+    _, _, _, leaf0, out0 = _run(cfg, monkeypatch, False)
+    assert rel_err(leaf, leaf0) < 2e-6
+    assert rel_err(out, out0) < 2e-6
+
+
+def test_mma_leaf_out_of_range_inputs_take_the_exact_path(monkeypatch):
+    cfg = CASES["gauss784"]
+    monkeypatch.setenv("DPK_LEAF_MMA", "1")
+    model = product_model(cfg, DEV, scale_grad=False)
+    orc = oracle_for(cfg)[0]  # fp32 oracle: nan_to_num(-inf) is -FLT_MAX there, like the reference
+    x, _ = pg.ratspn_inputs(cfg)
+    x[3, 5] = 1.0e4          # x^2 leaves the fp16 range
+    x[40, 700] = float("inf")
+    x[699, 0] = float("nan")
+    x[300:310, :] *= 300.0
+    out = model(x.to(DEV)).cpu()
+    ref = orc.log_prob(x)
+    assert rel_err(out, ref) < 1e-4
+
+
+def test_mma_leaf_huge_parameters_take_the_exact_path(monkeypatch):
+    cfg = CASES["gauss36"]
+    monkeypatch.setenv("DPK_LEAF_MMA", "1")
+    model = product_model(cfg, DEV, scale_grad=False)
+    orc, state = oracle_for(cfg)
+    with torch.no_grad():
+        model.base_layer.loc[2, 1, 0] = 1.0e5
+    state = dict(state)
+    state["base_layer.loc"] = model.base_layer.loc.detach().cpu().clone()
+    orc = orc.load_reference_state(state).double()
+    x, _ = pg.ratspn_inputs(cfg)
+    assert rel_err(model.base_layer(x.to(DEV)).cpu(), orc.leaf(x.double())) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["gauss784", "bern784", "gauss36"])
+def test_mma_gradients_match_float64_oracle(name, monkeypatch):
+    cfg = CASES[name]
+    monkeypatch.setenv("DPK_LEAF_MMA", "1")
+    model = product_model(cfg, DEV, scale_grad=False)
+    x, g = pg.ratspn_inputs(cfg)
+    with torch.enable_grad():
+        xd = x.to(DEV).requires_grad_(True)
+        out = model(xd)
+        (out * g.to(DEV)).sum().backward()
+    truth = oracle_for(cfg)[0].double().grads(x.double(), g.double(), clean_nan=True)
+    tol = 1e-4 + 4e-7 * float(truth["out"].abs().max())
+    key = "loc" if cfg["kind"] == "gaussian" else "logits"
+    mine = model.base_layer.loc.grad if cfg["kind"] == "gaussian" else model.base_layer.logits.grad
+    assert norm_err(mine, truth[key].float()) < tol
+    assert norm_err(xd.grad.cpu(), truth["x"].float()) < tol
+    assert norm_err(model.root_layer.weight.grad, truth["root"].float()) < tol
+
+
+def test_mma_full_batch_properties(monkeypatch):
+    """BASELINE config 2 at its full size (65536 x 784): size-independent checks -- the automatic path choice
+    agrees with the CUDA-core kernel, is invariant to a permutation of the batch, and a row of the big batch
+    equals the same row evaluated in a small batch."""
+    cfg = dict(CASES["gauss784"], batch=65536)
+    monkeypatch.delenv("DPK_LEAF_MMA", raising=False)
+    model = product_model(cfg, DEV, scale_grad=False)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn(65536, 784, device=DEV, generator=g)
+    out = model(x)
+    monkeypatch.setenv("DPK_LEAF_MMA", "0")
+    out0 = model(x)
+    assert rel_err(out, out0) < 2e-6
+    monkeypatch.delenv("DPK_LEAF_MMA", raising=False)
+    perm = torch.randperm(65536, device=DEV, generator=g)
+    assert rel_err(model(x[perm]), out[perm]) < 1e-6
+    monkeypatch.setenv("DPK_LEAF_MMA", "0")
+    assert rel_err(model(x[1000:1064]), out[1000:1064]) < 2e-6
