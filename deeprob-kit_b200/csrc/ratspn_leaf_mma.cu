@@ -315,24 +315,34 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     }
   } else {
     // ---------------- epilogue ----------------
+    // lanes = samples (TMEM lanes), registers = 32 consecutive columns: every store instruction writes one
+    // 128-byte line of the sample-minor activation tensor.  Per column the additive term is
+    // cst[column] + (-x^2/2)[region(column)][sample]; the per-column tables (constant, offset of the region
+    // inside this warp's staged x^2 block) are built once per unit so that the inner loop is
+    // 2 vector LDS per 4 columns + {LDS, 2 FADD, pointer add, STG} per column.
     const int et = threadIdx.x - kEpiThread0;   // 0..255
     const int ew = warp - 10;
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
     const int chalf = ew >> 2;                  // which 128 columns of the tile
     float* sqw = sqw_s + ew * (16 * 32);
+    const float* sqwl = sqw + lane;
     for (int it = 0; next_unit(it, &m, &j); ++it) {
       const bool isS = j < a.nS;
       const int col_base = (isS ? j : j - a.nS) * kMmaTileN;
       const int cols = (isS ? a.G0 : a.Ntot) - col_base;
       const bool quad = !isS && a.quad;
+      const bool mine = chalf * 128 < cols;       // this warp has columns in this tile
+      int g_lo = 0;
       if (!isS) {
-        const int n = col_base + et;
-        cst_s[et] = (n < a.Ntot) ? __ldg(a.cstm + n) : 0.f;
-        gcol_s[et] = (n < a.Ntot) ? n / a.K : a.G0 - 1;
+        const int n = min(col_base + et, a.Ntot - 1);
+        const int n_lo = min(col_base + (et & 128), a.Ntot - 1);   // first column of the half `et` belongs to
+        cst_s[et] = __ldg(a.cstm + n);
+        gcol_s[et] = quad ? (n / a.K - n_lo / a.K) * 32 : 0;        // word offset of the column's region in sqw
+        g_lo = min(col_base + chalf * 128, a.Ntot - 1) / a.K;
       }
       epi_bar();
-      // regions covered by this warp's 128 columns; their -x^2/2 sums are staged per (half, lane) in shared memory
-      const int g_lo = quad ? gcol_s[chalf * 128] : 0;
+      // more than 16 regions under 128 columns (K < 8): generic path that reads the x^2 sums from global memory
+      const bool wide = quad && gcol_s[chalf * 128 + min(127, max(0, cols - chalf * 128 - 1))] >= 16 * 32;
       float pre[16];
       auto preload = [&](int h) {
         const int64_t b = (int64_t)m * kMmaTileM + h * 128 + q * 32 + lane;
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         for (int r = 0; r < 16; ++r) sqw[r * 32 + lane] = pre[r];
         __syncwarp();
       };
-      if (quad && chalf * 128 < cols) {
+      if (quad && mine) {
         // the x^2 units of this M tile have smaller unit indices: they are running or done
         for (uint32_t spin = 0; ld_acquire(a.sq_ready + m) < a.nS; ++spin) {
           __nanosleep(64);
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       for (int h = 0; h < 2; ++h) {
         const int64_t b = (int64_t)m * kMmaTileM + h * 128 + q * 32 + lane;
         const bool bok = b < a.Bp;
-        if (quad && chalf * 128 < cols) {
+        if (quad && mine) {
           stage_pre();
           if (h == 0) preload(1);
         }
@@ -381,23 +391,49 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
               : "r"(taddr)
               : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int nvalid = min(32, cols - col0);
           if (isS) {
+            float* op = a.sq + (size_t)(col_base + col0) * a.Bp + b;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int g = col_base + col0 + i;
-              if (g < a.G0 && bok) a.sq[(size_t)g * a.Bp + b] = -0.5f * __uint_as_float(v[i]);
+              if (i < nvalid && bok) *op = -0.5f * __uint_as_float(v[i]);
+              op += a.Bp;
+            }
+          } else if (nvalid == 32 && bok && !wide) {
+            float* op = a.out + (size_t)(col_base + col0) * a.Bp + b;
+            const float4* c4 = reinterpret_cast<const float4*>(cst_s + col0);
+            const int4* o4 = reinterpret_cast<const int4*>(gcol_s + col0);
+            if (quad) {
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 c = c4[i4];
+                const int4 o = o4[i4];
+                __stcs(op, __uint_as_float(v[4 * i4 + 0]) + (c.x + sqwl[o.x])); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 1]) + (c.y + sqwl[o.y])); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 2]) + (c.z + sqwl[o.z])); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 3]) + (c.w + sqwl[o.w])); op += a.Bp;
+              }
+            } else {
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 c = c4[i4];
+                __stcs(op, __uint_as_float(v[4 * i4 + 0]) + c.x); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 1]) + c.y); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 2]) + c.z); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 3]) + c.w); op += a.Bp;
+              }
             }
           } else {
+            // partial tiles / rows past the padded batch / many regions per chunk: checked, generic
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int n = col_base + col0 + i;
-              if (n < a.Ntot && bok) {
+              if (i < nvalid && bok) {
                 float add = cst_s[col0 + i];
                 if (quad) {
-                  const int r = gcol_s[col0 + i] - g_lo;
+                  const int r = gcol_s[col0 + i] >> 5;
                   add += (r < 16) ? sqw[r * 32 + lane] : __ldcg(a.sq + (size_t)(g_lo + r) * a.Bp + b);
                 }
-                __stcs(a.out + (size_t)n * a.Bp + b, __uint_as_float(v[i]) + add);
+                __stcs(a.out + (size_t)(col_base + col0 + i) * a.Bp + b, __uint_as_float(v[i]) + add);
               }
             }
           }
