@@ -52,6 +52,8 @@ struct LeafMmaArgs {
   int64_t B, Bp;
   int D, quad, G0, K, Ntot;
   int nS, nW, KBn, last_ks, nM;
+  int mma_mode;               // 0 plain tcgen05.mma, 1 weight-stationary form (B operand collector)
+  int look;                   // x^2 units run `look` M tiles ahead of the W units that consume them
   const unsigned char* wimg;  // [nW][KBn][hi | lo][16 KB]
   const unsigned char* simg;  // [nS][KBn][16 KB] region indicator (exact in fp16)
   const float* cstm;          // [Ntot] additive constant of every column
@@ -62,6 +64,7 @@ struct LeafMmaArgs {
   int* unit_counter;          // dynamic scheduler (zeroed before the launch)
   int* sq_ready;              // [nM] number of finished x^2 units of every M tile (zeroed before the launch)
   float xlimit;
+  unsigned long long* stats;  // debug (DPK_MMA_STATS=1): cycles per role spent waiting, else NULL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,6 +115,30 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The issuing thread is on the critical path (one tcgen05.mma per 128 cycles at full rate), so the issue
+// sequence is kept minimal: the 64-bit shared-memory descriptors differ only in their low word (address >> 4),
+// which is computed warp-uniformly outside the elected branch, passed as a 32-bit register and glued to the
+// constant high word inside the asm block.
+// Variants: plain; weight-stationary (.ws) with the B operand (256 columns = 8 KB) kept in collector buffer
+// b0 / b1 and re-used by the following instructions instead of being read from shared memory again.
+// high word of the descriptor: SBO = 512 B (8 rows x 64 B), version 1, SWIZZLE_64B; low word = (addr >> 4) | LBO(1) << 16
+constexpr uint32_t kDescHi = (512u >> 4) | (1u << 14) | (4u << 29);
+#define DPK_TC_MMA_VARIANT(name, opcode)                                                                     \
+  __device__ __forceinline__ void name(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,       \
+                                       uint32_t accumulate) {                                               \
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"                  \
+                 "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t" opcode " [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem), \
+                 "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)                             \
+                 : "memory");                                                                               \
+  }
+DPK_TC_MMA_VARIANT(tc_mma_lo, "tcgen05.mma.cta_group::1.kind::f16")
+DPK_TC_MMA_VARIANT(tc_mma_ws_fill0, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill")
+DPK_TC_MMA_VARIANT(tc_mma_ws_use0, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use")
+DPK_TC_MMA_VARIANT(tc_mma_ws_last0, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse")
+DPK_TC_MMA_VARIANT(tc_mma_ws_fill1, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::fill")
+DPK_TC_MMA_VARIANT(tc_mma_ws_last1, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::lastuse")
+#undef DPK_TC_MMA_VARIANT
+
 // K-major operand, 64-byte swizzle: rows 64 B apart, 8-row groups 512 B apart (SBO), descriptor version 1
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
@@ -128,7 +155,31 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
                : "l"(p));
   return v;
 }
+// true in exactly one (elected) lane of a converged warp; ptxas treats the guarded region as single-threaded
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Unit order: the x^2 (S) units of M tile t are issued `look` tiles before the W units of that tile, so
+// that their sums are long finished when a W epilogue needs them (and the x tile is already in L2):
+//   [S(0)] .. [S(look-1)]  [S(look) W(0)] .. [S(nM-1) W(nM-1-look)]  [W(nM-look)] .. [W(nM-1)]
+__device__ __forceinline__ void decode_unit(int u, int nS, int nW, int nM, int look, int* m, int* j) {
+  const int head = look * nS;
+  if (u < head) { *m = u / nS; *j = u - *m * nS; return; }
+  u -= head;
+  const int upm = nS + nW, mid = (nM - look) * upm;
+  if (u < mid) {
+    const int t = u / upm, r = u - t * upm;
+    if (r < nS) { *m = look + t; *j = r; } else { *m = t; *j = r; }
+    return;
+  }
+  u -= mid;
+  const int t = u / nW;
+  *m = nM - look + t; *j = nS + (u - t * nW);
+}
 
 constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units behind the scheduler (3 stages + 2)
 
@@ -185,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     mbar_wait(sfull + (it & (kSchedSlots - 1)), (uint32_t)(it / kSchedSlots) & 1u);
     const int u = sched_s[it & (kSchedSlots - 1)];
     if (u < 0) return false;
-    *m = u / upm; *j = u - *m * upm;
+    decode_unit(u, a.nS, a.nW, a.nM, a.look, m, j);
     return true;
   };
   int m, j;
@@ -203,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       }
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u < 0) break;
-      m = u / upm; j = u - m * upm;
+      decode_unit(u, a.nS, a.nW, a.nM, a.look, &m, &j);
       const bool isS = j < a.nS;
       const unsigned char* src = isS ? a.simg + (size_t)j * a.KBn * kImg : a.wimg + (size_t)(j - a.nS) * a.KBn * (2 * kImg);
       const uint32_t bytes = isS ? kImg : 2 * kImg;
@@ -220,32 +271,60 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   } else if (warp == 1) {
     // ---------------- MMA issue (one thread) ----------------
     int stage = 0; uint32_t phase = 0;
-    for (int it = 0; next_unit(it, &m, &j); ++it) {
+    long long w_tempty = 0, w_full = 0, w_sched = 0;
+    const long long t_begin = clock64();
+    for (int it = 0;; ++it) {
+      long long t0 = a.stats ? clock64() : 0;
+      if (!next_unit(it, &m, &j)) break;
+      if (a.stats) w_sched += clock64() - t0;
       const bool isS = j < a.nS;
       const int cols = isS ? a.G0 - j * kMmaTileN : a.Ntot - (j - a.nS) * kMmaTileN;
       const int N = min(kMmaTileN, (cols + 15) / 16 * 16);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);  // fp32 accum, fp16 A/B, K-major, M=128
       if (lane == 0) {
+        t0 = a.stats ? clock64() : 0;
         if (it > 0) mbar_wait(tempty, (uint32_t)(it - 1) & 1u);
+        if (a.stats) w_tempty += clock64() - t0;
         tc_fence_after();
       }
+      // weight-stationary issue needs N in {64, 128, 256}
+      const bool ws = a.mma_mode == 1 && (N == 64 || N == 128 || N == 256);
       for (int kb = 0; kb < a.KBn; ++kb) {
-        if (lane == 0) {
-          mbar_wait(full + stage, phase);
-          tc_fence_after();
-          const uint32_t sa = base + stage * kStage;
-          const int nks = (kb == a.KBn - 1) ? a.last_ks : 2;
-          for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t b_hi = smem_desc_sw64(sa + 2 * kImg + ks * 32);
-            const uint64_t b_lo = smem_desc_sw64(sa + 3 * kImg + ks * 32);
+        t0 = a.stats ? clock64() : 0;
+        mbar_wait(full + stage, phase);          // whole warp: keeps everything below warp-uniform
+        if (a.stats) w_full += clock64() - t0;
+        tc_fence_after();
+        // low descriptor words of the stage's four images: A hi | A lo | B hi | B lo (each 16 KB = 0x400 units)
+        const uint32_t lo0 = ((base + stage * kStage) >> 4) | (1u << 16);
+        const int nks = (kb == a.KBn - 1) ? a.last_ks : 2;
+        if (elect_one()) {
+          const uint32_t d0 = tmem, d1 = tmem + kMmaTileN;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint64_t a_hi = smem_desc_sw64(sa + h * (kImg / 2) + ks * 32);
-              const uint64_t a_lo = smem_desc_sw64(sa + kImg + h * (kImg / 2) + ks * 32);
-              const uint32_t d = tmem + h * kMmaTileN;
-              tc_mma(d, a_hi, b_hi, idesc, (kb | ks) != 0);
-              tc_mma(d, a_lo, b_hi, idesc, 1u);
-              if (!isS) tc_mma(d, a_hi, b_lo, idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {
+            if (ks < nks) {
+              const uint32_t a_hi0 = lo0 + 2 * ks, a_hi1 = a_hi0 + (kImg / 32);
+              const uint32_t a_lo0 = a_hi0 + (kImg / 16), a_lo1 = a_lo0 + (kImg / 32);
+              const uint32_t b_hi = a_hi0 + 2 * (kImg / 16), b_lo = a_hi0 + 3 * (kImg / 16);
+              const uint32_t acc = (kb | ks) != 0;
+              if (ws) {                 // b_hi read once for 4 instructions, b_lo once for 2
+                tc_mma_ws_fill0(d0, a_hi0, b_hi, idesc, acc);
+                tc_mma_ws_use0(d1, a_hi1, b_hi, idesc, acc);
+                tc_mma_ws_use0(d0, a_lo0, b_hi, idesc, 1u);
+                tc_mma_ws_last0(d1, a_lo1, b_hi, idesc, 1u);
+                if (!isS) {
+                  tc_mma_ws_fill1(d0, a_hi0, b_lo, idesc, 1u);
+                  tc_mma_ws_last1(d1, a_hi1, b_lo, idesc, 1u);
+                }
+              } else {
+                tc_mma_lo(d0, a_hi0, b_hi, idesc, acc);
+                tc_mma_lo(d1, a_hi1, b_hi, idesc, acc);
+                tc_mma_lo(d0, a_lo0, b_hi, idesc, 1u);
+                tc_mma_lo(d1, a_lo1, b_hi, idesc, 1u);
+                if (!isS) {
+                  tc_mma_lo(d0, a_hi0, b_lo, idesc, 1u);
+                  tc_mma_lo(d1, a_hi1, b_lo, idesc, 1u);
+                }
+              }
             }
           }
           tc_commit(empty + stage);
@@ -254,6 +333,12 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         __syncwarp();
         if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
       }
+    }
+    if (a.stats && lane == 0) {
+      atomicAdd(a.stats + 0, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(a.stats + 1, (unsigned long long)w_tempty);
+      atomicAdd(a.stats + 2, (unsigned long long)w_full);
+      atomicAdd(a.stats + 3, (unsigned long long)w_sched);
     }
   } else if (warp < 10) {
     // ---------------- operand converters ----------------
@@ -273,7 +358,9 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         }
       };
       auto convert = [&](float4 (&buf)[8]) {
+        const long long t0 = a.stats ? clock64() : 0;
         mbar_wait(empty + stage, phase ^ 1u);
+        if (a.stats && threadIdx.x == 64) atomicAdd(a.stats + 4, (unsigned long long)(clock64() - t0));
         unsigned char* A = sm + stage * kStage;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -364,7 +451,9 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         }
         preload(0);
       }
+      const long long t_w0 = a.stats ? clock64() : 0;
       mbar_wait(tfull, (uint32_t)it & 1u);
+      const long long t_w1 = a.stats ? clock64() : 0;
       tc_fence_after();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
@@ -442,6 +531,11 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty);
+      if (a.stats && threadIdx.x == kEpiThread0) {
+        atomicAdd(a.stats + 5, (unsigned long long)(t_w1 - t_w0));                    // waiting for the accumulators
+        atomicAdd(a.stats + (isS ? 7 : 6), (unsigned long long)(clock64() - t_w1));   // draining them
+        atomicAdd(a.stats + (isS ? 9 : 8), 1ull);
+      }
       if (isS) __threadfence();   // x^2 sums: visible device-wide before the ready counter moves
       epi_bar();
       if (isS && et == 0) atomicAdd(a.sq_ready + m, 1);
@@ -540,6 +634,8 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.nS = p.mma_nS; a.nW = p.mma_nW; a.KBn = p.mma_kb;
   a.last_ks = ((p.D + 15) / 16) % 2 == 1 ? 1 : 2;
   a.nM = (int)ceil_div(p.B, kMmaTileM);
+  a.mma_mode = env_int("DPK_MMA_MODE", 1);
+  a.look = a.nS > 0 ? std::min(a.nM, env_int("DPK_MMA_LOOKAHEAD", 32)) : 0;
   a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_wimg);
   a.simg = reinterpret_cast<const unsigned char*>(ws + p.off_simg);
   a.cstm = ws + p.off_cstm;
@@ -550,12 +646,26 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.unit_counter = a.redo + p.Bp / 32 + 1;
   a.sq_ready = a.redo + p.Bp / 32 + 2;
   a.xlimit = a.quad ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
+  const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
+  a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.sq_ready + a.nM + (a.nM & 1)) : nullptr;
+  if (want_stats) DPK_CUDA_TRY(cudaMemsetAsync(a.stats, 0, 16 * 8, st));
   const int n_units = a.nM * (a.nS + a.nW);
-  const int grid = std::min(sm_count(), n_units);
+  const int grid = std::min(std::min(sm_count(), env_int("DPK_MMA_GRID", 1 << 30)), n_units);
   const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ratspn_leaf_mma_kernel<<<grid, kThreads, smem, st>>>(a);
   DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel");
+  if (want_stats) {   // debug only: synchronises
+    unsigned long long h[16];
+    DPK_CUDA_TRY(cudaMemcpyAsync(h, a.stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    DPK_CUDA_TRY(cudaStreamSynchronize(st));
+    const double g = grid;
+    fprintf(stderr, "[mma stats] B=%lld per CTA: mma-warp total %.0f  wait tmem-empty %.0f  wait full %.0f  wait sched %.0f | "
+                    "converter wait empty %.0f | epilogue wait tmem-full %.0f  drain W %.0f (%llu units, %.0f/unit)  "
+                    "drain S %.0f (%llu units)\n", (long long)p.B,
+            h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[8], h[8] ? (double)h[6] / h[8] : 0.0,
+            h[7] / g, h[9]);
+  }
   return DPK_OK;
 }
 

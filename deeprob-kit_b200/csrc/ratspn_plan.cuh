@@ -160,7 +160,7 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
       p->off_simg = take((size_t)p->mma_nS * p->mma_kb * img_floats);   // directly behind wimg (one memset)
       p->off_cstm = take((size_t)p->G0 * p->K);
       p->off_sq = take((size_t)p->G0 * p->Bp);
-      p->off_mflags = take((size_t)p->Bp / 32 + 2 + (size_t)ceil_div(p->B, kMmaTileM));
+      p->off_mflags = take((size_t)p->Bp / 32 + 2 + (size_t)ceil_div(p->B, kMmaTileM) + 1 + 32);  // + debug stats
     }
   }
   for (int l = 0; l < p->depth; ++l) {
