@@ -16,21 +16,28 @@
 // split is exact (NaN = marginalised, inf, |x| > limit) flag their 32-sample group, which the exact
 // CUDA-core kernel (ratspn_leaf.cu) then redoes; parameters outside the fp16 range flag everything.
 //
+// Two launches of one kernel template:
+//   PREP = true   (one unit per 256-sample M tile and 256-region tile)  splits x once into its hi/lo fp16
+//                 operand images (global scratch, 64B-swizzled K-major, exactly the shared-memory layout), flags
+//                 out-of-range inputs and -- for the Gaussian -- runs the x^2 GEMM whose epilogue stores the
+//                 per-(region, sample) term -x^2/2;
+//   PREP = false  (one unit per M tile and 256-column weight tile)  the main GEMM: both operands are now plain
+//                 copies, the epilogue adds the per-column constant and the -x^2/2 term and writes act[0].
 // Kernel shape: persistent, one CTA per SM, 18 warps:
-//   warp 0      bulk-copy (TMA 1-D, UBLKCP) producer of the pre-swizzled weight images
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue
-//   warps 2-9   operand converters: coalesced 16-byte loads of x, hi/lo split, 64B-swizzled K-major stores
-//   warps 10-17 epilogue: tcgen05.ld, + per-column constant, + per-region -x^2/2, coalesced stores into
-//               the sample-minor activation layout act[0] = [G0*K][Bp]
-// Units are handed out in increasing order by an atomic counter (warp 0 publishes the unit through a small
-// shared-memory ring), M-tile-major with the x^2 units of an M tile first: CTAs that run at the same time
-// work on the same few M tiles, so x is read from HBM once and re-read from L2, and the load is balanced
-// dynamically.  W units read the x^2 sums of their M tile from a global scratch guarded by a per-M-tile
-// ready counter; the unit that produces them always has a smaller index, i.e. is already running.
-// A unit of work = (256-sample M tile, 256-column N tile): two M=128 accumulators of 256 fp32 columns
-// (all 512 TMEM columns) share every weight stage, so the 4 MB weight image is streamed once per 256
-// samples.  K is walked in 32-feature blocks through a 3-stage ring of {A hi, A lo, B hi, B lo} 16 KB
-// images synchronised with mbarriers (full: 8 converter warps + expect_tx bytes; empty: tcgen05.commit).
+//   warp 0      unit scheduler (atomic counter -> shared-memory ring) + bulk-copy (TMA 1-D, UBLKCP) producer of the
+//               pre-swizzled weight images
+//   warp 1      TMEM allocation + tcgen05.mma issue by one elected thread
+//   warps 2-9   operand feeders.  PREP: coalesced 16-byte loads of x, hi/lo split, swizzled stores (x^2 images to
+//               shared memory, x images to global).  Main: 16-byte copies L2 -> registers -> shared memory of the
+//               x images, 1.5 stages in flight per thread
+//   warps 10-17 epilogue: tcgen05.ld, + per-column constant, + per-region -x^2/2, coalesced stores into the
+//               sample-minor activation layout act[0] = [G0*K][Bp]
+// Units are handed out in increasing order by an atomic counter, M-tile-major: CTAs that run at the same time
+// work on the same few M tiles, so the x images are read from L2, and the load is balanced dynamically.
+// A unit = (256-sample M tile, 256-column N tile): two M=128 accumulators of 256 fp32 columns (all 512 TMEM
+// columns) share every weight stage, so the 4 MB weight image is streamed once per 256 samples.  K is walked in
+// 32-feature blocks through a 3-stage ring of {A hi, A lo, B hi, B lo} 16 KB images synchronised with mbarriers
+// (full: 8 feeder warps + expect_tx bytes; empty: tcgen05.commit).
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -53,7 +60,6 @@ struct LeafMmaArgs {
   int D, quad, G0, K, Ntot;
   int nS, nW, KBn, last_ks, nM;
   int mma_mode;               // 0 plain tcgen05.mma, 1 weight-stationary form (B operand collector)
-  int look;                   // x^2 units run `look` M tiles ahead of the W units that consume them
   const unsigned char* wimg;  // [nW][KBn][hi | lo][16 KB]
   const unsigned char* simg;  // [nS][KBn][16 KB] region indicator (exact in fp16)
   const float* cstm;          // [Ntot] additive constant of every column
@@ -61,8 +67,8 @@ struct LeafMmaArgs {
   float* out;                 // [Ntot][Bp]
   int* redo;                  // [Bp/32] groups the exact kernel must redo
   const int* wflag;           // != 0: parameters not representable, redo everything
-  int* unit_counter;          // dynamic scheduler (zeroed before the launch)
-  int* sq_ready;              // [nM] number of finished x^2 units of every M tile (zeroed before the launch)
+  int* unit_counter;          // [2] dynamic scheduler of the two launches (zeroed before)
+  unsigned char* aimg;        // [nM][KBn][hi | lo][16 KB] fp16 split of x in operand layout, written by the PREP launch
   float xlimit;
   unsigned long long* stats;  // debug (DPK_MMA_STATS=1): cycles per role spent waiting, else NULL
 };
@@ -105,16 +111,6 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], fp16 operands, fp32 accumulate, M = 128, N from the instruction descriptor
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // The issuing thread is on the critical path (one tcgen05.mma per 128 cycles at full rate), so the issue
 // sequence is kept minimal: the 64-bit shared-memory descriptors differ only in their low word (address >> 4),
 // which is computed warp-uniformly outside the elected branch, passed as a 32-bit register and glued to the
@@ -139,11 +135,7 @@ DPK_TC_MMA_VARIANT(tc_mma_ws_fill1, "tcgen05.mma.ws.cta_group::1.kind::f16.colle
 DPK_TC_MMA_VARIANT(tc_mma_ws_last1, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::lastuse")
 #undef DPK_TC_MMA_VARIANT
 
-// K-major operand, 64-byte swizzle: rows 64 B apart, 8-row groups 512 B apart (SBO), descriptor version 1
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
-         (4ull << 61);
-}
+// Operand images are K-major with the 64-byte swizzle: rows 64 B apart, 8-row groups 512 B apart (SBO).
 // byte offset of 16-byte chunk `c` (0..3) of row `row` inside a 64B-swizzled image
 __host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t c) {
   return row * 64u + ((c ^ ((row >> 1) & 3u)) << 4);
@@ -163,32 +155,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// Unit order: the x^2 (S) units of M tile t are issued `look` tiles before the W units of that tile, so
-// that their sums are long finished when a W epilogue needs them (and the x tile is already in L2):
-//   [S(0)] .. [S(look-1)]  [S(look) W(0)] .. [S(nM-1) W(nM-1-look)]  [W(nM-look)] .. [W(nM-1)]
-__device__ __forceinline__ void decode_unit(int u, int nS, int nW, int nM, int look, int* m, int* j) {
-  const int head = look * nS;
-  if (u < head) { *m = u / nS; *j = u - *m * nS; return; }
-  u -= head;
-  const int upm = nS + nW, mid = (nM - look) * upm;
-  if (u < mid) {
-    const int t = u / upm, r = u - t * upm;
-    if (r < nS) { *m = look + t; *j = r; } else { *m = t; *j = r; }
-    return;
-  }
-  u -= mid;
-  const int t = u / nW;
-  *m = nM - look + t; *j = nS + (u - t * nW);
-}
-
 constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units behind the scheduler (3 stages + 2)
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
+template <bool PREP>
 __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const LeafMmaArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -198,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   int* gcol_s = reinterpret_cast<int*>(cst_s + kMmaTileN);
   float* sqw_s = reinterpret_cast<float*>(gcol_s + kMmaTileN);        // [8 epilogue warps][16 regions][32 lanes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sqw_s + 8 * 16 * 32);
-  uint64_t* full = bars;                 // [stages] A converted (8 warps) + B landed (tx bytes)
+  uint64_t* full = bars;                 // [stages] A staged (8 warps) + B landed (tx bytes)
   uint64_t* empty = bars + kMmaStages;   // [stages] MMAs that read the stage have completed
   uint64_t* tfull = bars + 2 * kMmaStages;   // accumulators of the unit complete
   uint64_t* tempty = tfull + 1;              // epilogue drained the accumulators
@@ -206,10 +175,13 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   int* sched_s = reinterpret_cast<int*>(sfull + kSchedSlots);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_s + kSchedSlots);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the Gaussian PREP launch and the main launch run GEMMs; the Bernoulli PREP launch only converts
+  const bool tensor = !PREP || a.quad != 0;
 
   if (__ldg(a.wflag) != 0) {  // parameters outside the fp16 range: the exact kernel does everything
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.Bp / 32; i += (int64_t)gridDim.x * blockDim.x)
-      a.redo[i] = 1;
+    if (PREP)
+      for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.Bp / 32; i += (int64_t)gridDim.x * blockDim.x)
+        a.redo[i] = 1;
     return;
   }
 
@@ -229,14 +201,15 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int upm = a.nS + a.nW;
+  // units of this launch: (M tile m, N tile j), M-tile-major
+  const int upm = PREP ? max(a.nS, 1) : a.nW;
   const int n_units = a.nM * upm;
   // every role walks the same unit sequence: entry `it` of the scheduler ring
   auto next_unit = [&](int it, int* m, int* j) -> bool {
     mbar_wait(sfull + (it & (kSchedSlots - 1)), (uint32_t)(it / kSchedSlots) & 1u);
     const int u = sched_s[it & (kSchedSlots - 1)];
     if (u < 0) return false;
-    decode_unit(u, a.nS, a.nW, a.nM, a.look, m, j);
+    *m = u / upm; *j = u - *m * upm;
     return true;
   };
   int m, j;
@@ -247,17 +220,17 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     for (int it = 0;; ++it) {
       int u = 0;
       if (lane == 0) {
-        u = atomicAdd(a.unit_counter, 1);
+        u = atomicAdd(a.unit_counter + (PREP ? 0 : 1), 1);
         if (u >= n_units) u = -1;
         sched_s[it & (kSchedSlots - 1)] = u;
         mbar_arrive(sfull + (it & (kSchedSlots - 1)));   // release: the store above is visible to the waiters
       }
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u < 0) break;
-      decode_unit(u, a.nS, a.nW, a.nM, a.look, &m, &j);
-      const bool isS = j < a.nS;
-      const unsigned char* src = isS ? a.simg + (size_t)j * a.KBn * kImg : a.wimg + (size_t)(j - a.nS) * a.KBn * (2 * kImg);
-      const uint32_t bytes = isS ? kImg : 2 * kImg;
+      if (!tensor) continue;
+      m = u / upm; j = u - m * upm;
+      const unsigned char* src = PREP ? a.simg + (size_t)j * a.KBn * kImg : a.wimg + (size_t)j * a.KBn * (2 * kImg);
+      const uint32_t bytes = PREP ? kImg : 2 * kImg;
       for (int kb = 0; kb < a.KBn; ++kb) {
         if (lane == 0) {
           mbar_wait(empty + stage, phase ^ 1u);
@@ -269,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issue (one thread) ----------------
+    // ---------------- MMA issue (one elected thread) ----------------
     int stage = 0; uint32_t phase = 0;
     long long w_tempty = 0, w_full = 0, w_sched = 0;
     const long long t_begin = clock64();
@@ -277,16 +250,14 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       long long t0 = a.stats ? clock64() : 0;
       if (!next_unit(it, &m, &j)) break;
       if (a.stats) w_sched += clock64() - t0;
-      const bool isS = j < a.nS;
-      const int cols = isS ? a.G0 - j * kMmaTileN : a.Ntot - (j - a.nS) * kMmaTileN;
+      if (!tensor) continue;
+      const int cols = (PREP ? a.G0 : a.Ntot) - j * kMmaTileN;
       const int N = min(kMmaTileN, (cols + 15) / 16 * 16);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);  // fp32 accum, fp16 A/B, K-major, M=128
-      if (lane == 0) {
-        t0 = a.stats ? clock64() : 0;
-        if (it > 0) mbar_wait(tempty, (uint32_t)(it - 1) & 1u);
-        if (a.stats) w_tempty += clock64() - t0;
-        tc_fence_after();
-      }
+      t0 = a.stats ? clock64() : 0;
+      if (it > 0) mbar_wait(tempty, (uint32_t)(it - 1) & 1u);
+      if (a.stats) w_tempty += clock64() - t0;
+      tc_fence_after();
       // weight-stationary issue needs N in {64, 128, 256}
       const bool ws = a.mma_mode == 1 && (N == 64 || N == 128 || N == 256);
       for (int kb = 0; kb < a.KBn; ++kb) {
@@ -311,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
                 tc_mma_ws_use0(d1, a_hi1, b_hi, idesc, acc);
                 tc_mma_ws_use0(d0, a_lo0, b_hi, idesc, 1u);
                 tc_mma_ws_last0(d1, a_lo1, b_hi, idesc, 1u);
-                if (!isS) {
+                if (!PREP) {
                   tc_mma_ws_fill1(d0, a_hi0, b_lo, idesc, 1u);
                   tc_mma_ws_last1(d1, a_hi1, b_lo, idesc, 1u);
                 }
@@ -320,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
                 tc_mma_lo(d1, a_hi1, b_hi, idesc, acc);
                 tc_mma_lo(d0, a_lo0, b_hi, idesc, 1u);
                 tc_mma_lo(d1, a_lo1, b_hi, idesc, 1u);
-                if (!isS) {
+                if (!PREP) {
                   tc_mma_lo(d0, a_hi0, b_lo, idesc, 1u);
                   tc_mma_lo(d1, a_hi1, b_lo, idesc, 1u);
                 }
@@ -335,72 +306,129 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       }
     }
     if (a.stats && lane == 0) {
-      atomicAdd(a.stats + 0, (unsigned long long)(clock64() - t_begin));
-      atomicAdd(a.stats + 1, (unsigned long long)w_tempty);
-      atomicAdd(a.stats + 2, (unsigned long long)w_full);
-      atomicAdd(a.stats + 3, (unsigned long long)w_sched);
+      unsigned long long* st = a.stats + (PREP ? 16 : 0);
+      atomicAdd(st + 0, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(st + 1, (unsigned long long)w_tempty);
+      atomicAdd(st + 2, (unsigned long long)w_full);
+      atomicAdd(st + 3, (unsigned long long)w_sched);
     }
   } else if (warp < 10) {
-    // ---------------- operand converters ----------------
-    const int cw = warp - 2;
-    const int c8 = lane & 7, rsub = lane >> 3;
+    // ---------------- operand feeders ----------------
+    const int ft = threadIdx.x - 64;            // 0..255
     int stage = 0; uint32_t phase = 0;
+    auto wait_empty = [&]() {
+      const long long t0 = a.stats ? clock64() : 0;
+      mbar_wait(empty + stage, phase ^ 1u);
+      if (a.stats && ft == 0) atomicAdd(a.stats + (PREP ? 16 : 0) + 4, (unsigned long long)(clock64() - t0));
+    };
+    auto publish = [&]() {                      // generic-proxy stores -> visible to the MMA (async proxy)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + stage);
+      if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
+    };
     for (int it = 0; next_unit(it, &m, &j); ++it) {
-      const bool isS = j < a.nS;
-      const bool check = (j == 0);
-      const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
-      auto load = [&](int kb, float4 (&v)[8]) {
-        const int f0 = kb * kMmaKB + c8 * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t b = b0 + 4 * i;
-          v[i] = (b < a.B && f0 < a.D) ? ldg_stream(a.x + b * a.D + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      auto convert = [&](float4 (&buf)[8]) {
-        const long long t0 = a.stats ? clock64() : 0;
-        mbar_wait(empty + stage, phase ^ 1u);
-        if (a.stats && threadIdx.x == 64) atomicAdd(a.stats + 4, (unsigned long long)(clock64() - t0));
-        unsigned char* A = sm + stage * kStage;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 v = buf[i];
-          if (check) {
-            const bool bad = !(fabsf(v.x) <= a.xlimit) || !(fabsf(v.y) <= a.xlimit) || !(fabsf(v.z) <= a.xlimit) ||
-                             !(fabsf(v.w) <= a.xlimit);
-            if (bad) a.redo[(b0 + 4 * i) >> 5] = 1;
-          }
-          if (isS) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
+      unsigned char* gimg = a.aimg + (size_t)m * a.KBn * (2 * kImg);
+      if constexpr (PREP) {
+        const int cw = warp - 2;
+        const int c8 = lane & 7, rsub = lane >> 3;
+        const bool first = (j == 0);            // splits x for the whole M tile and checks its range
+        const bool sq = a.quad != 0;            // feeds the x^2 GEMM of this unit through shared memory
+        const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
+        auto split = [](const float4& v, uint2* hv, uint2* lv) {
           const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
           const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
           const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
-          const uint32_t row = cw * 32 + 4 * i + rsub;
-          const uint32_t off = sw64_off(row, c8 >> 1) + (c8 & 1) * 8;
-          uint2 hv, lv;
-          hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
-          lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
-          *reinterpret_cast<uint2*>(A + off) = hv;
-          *reinterpret_cast<uint2*>(A + kImg + off) = lv;
+          hv->x = *reinterpret_cast<const uint32_t*>(&h0); hv->y = *reinterpret_cast<const uint32_t*>(&h1);
+          lv->x = *reinterpret_cast<const uint32_t*>(&l0); lv->y = *reinterpret_cast<const uint32_t*>(&l1);
+        };
+        auto load = [&](int kb, float4 (&v)[8]) {
+          const int f0 = kb * kMmaKB + c8 * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t b = b0 + 4 * i;
+            v[i] = (b < a.B && f0 < a.D) ? ldg_stream(a.x + b * a.D + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        auto convert = [&](int kb, float4 (&buf)[8]) {
+          if (sq) wait_empty();
+          unsigned char* A = sm + stage * kStage;
+          unsigned char* G = gimg + (size_t)kb * (2 * kImg);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v = buf[i];
+            const uint32_t row = cw * 32 + 4 * i + rsub;
+            const uint32_t off = sw64_off(row, c8 >> 1) + (c8 & 1) * 8;
+            uint2 hv, lv;
+            if (first) {
+              const bool bad = !(fabsf(v.x) <= a.xlimit) || !(fabsf(v.y) <= a.xlimit) || !(fabsf(v.z) <= a.xlimit) ||
+                               !(fabsf(v.w) <= a.xlimit);
+              if (bad) a.redo[(b0 + 4 * i) >> 5] = 1;
+              split(v, &hv, &lv);
+              *reinterpret_cast<uint2*>(G + off) = hv;
+              *reinterpret_cast<uint2*>(G + kImg + off) = lv;
+            }
+            if (sq) {
+              v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w;
+              split(v, &hv, &lv);
+              *reinterpret_cast<uint2*>(A + off) = hv;
+              *reinterpret_cast<uint2*>(A + kImg + off) = lv;
+            }
+          }
+          if (sq) publish();
+        };
+        // two register sets, loads two K blocks ahead of their use (no register copies: a copy would wait for the load)
+        float4 bufA[8], bufB[8];
+        load(0, bufA);
+        if (a.KBn > 1) load(1, bufB);
+        for (int kb = 0; kb < a.KBn; kb += 2) {
+          convert(kb, bufA);
+          if (kb + 2 < a.KBn) load(kb + 2, bufA);
+          if (kb + 1 < a.KBn) {
+            convert(kb + 1, bufB);
+            if (kb + 3 < a.KBn) load(kb + 3, bufB);
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full + stage);
-        if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
-      };
-      // two register sets, loads two K blocks ahead of their use (no register copies: a copy would wait for the load)
-      float4 bufA[8], bufB[8];
-      load(0, bufA);
-      if (a.KBn > 1) load(1, bufB);
-      for (int kb = 0; kb < a.KBn; kb += 2) {
-        convert(bufA);
-        if (kb + 2 < a.KBn) load(kb + 2, bufA);
-        if (kb + 1 < a.KBn) {
-          convert(bufB);
-          if (kb + 3 < a.KBn) load(kb + 3, bufB);
+      } else {
+        // copy the x images of this M tile into the A half of every stage.  Thread t moves bytes
+        // [16 t + 4096 i, +16), i = 0..7, of each 32 KB stage image, handled as two groups of 4 pieces; three
+        // groups (1.5 stages, 48 registers) are in flight per thread.  Explicit scalars: a load destination must
+        // never be spilled or copied (either would wait for the load and kill the prefetch).
+        const uint4* src = reinterpret_cast<const uint4*>(gimg) + ft;
+        const int NG = 2 * a.KBn;
+#define DPK_FETCH(G, n)                                                                           \
+  {                                                                                               \
+    const uint4* p_ = src + (size_t)((n) >> 1) * (2 * kImg / 16) + ((n) & 1) * 1024;              \
+    G##0 = __ldcg(p_); G##1 = __ldcg(p_ + 256); G##2 = __ldcg(p_ + 512); G##3 = __ldcg(p_ + 768); \
+  }
+#define DPK_STORE(G, n)                                                                           \
+  {                                                                                               \
+    if (((n) & 1) == 0) wait_empty();                                                             \
+    uint4* d_ = reinterpret_cast<uint4*>(sm + stage * kStage) + ft + ((n) & 1) * 1024;            \
+    d_[0] = G##0; d_[256] = G##1; d_[512] = G##2; d_[768] = G##3;                                 \
+    if ((n) & 1) publish();                                                                       \
+  }
+        uint4 a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3;
+        DPK_FETCH(a, 0)
+        DPK_FETCH(b, 1)
+        if (2 < NG) DPK_FETCH(c, 2)
+        for (int n = 0; n < NG; n += 3) {
+          DPK_STORE(a, n)
+          if (n + 3 < NG) DPK_FETCH(a, n + 3)
+          if (n + 1 < NG) {
+            DPK_STORE(b, n + 1)
+            if (n + 4 < NG) DPK_FETCH(b, n + 4)
+          }
+          if (n + 2 < NG) {
+            DPK_STORE(c, n + 2)
+            if (n + 5 < NG) DPK_FETCH(c, n + 5)
+          }
         }
+#undef DPK_FETCH
+#undef DPK_STORE
       }
     }
-  } else {
+  } else if (tensor) {
     // ---------------- epilogue ----------------
     // lanes = samples (TMEM lanes), registers = 32 consecutive columns: every store instruction writes one
     // 128-byte line of the sample-minor activation tensor.  Per column the additive term is
@@ -414,8 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     float* sqw = sqw_s + ew * (16 * 32);
     const float* sqwl = sqw + lane;
     for (int it = 0; next_unit(it, &m, &j); ++it) {
-      const bool isS = j < a.nS;
-      const int col_base = (isS ? j : j - a.nS) * kMmaTileN;
+      constexpr bool isS = PREP;
+      const int col_base = j * kMmaTileN;
       const int cols = (isS ? a.G0 : a.Ntot) - col_base;
       const bool quad = !isS && a.quad;
       const bool mine = chalf * 128 < cols;       // this warp has columns in this tile
@@ -443,14 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         for (int r = 0; r < 16; ++r) sqw[r * 32 + lane] = pre[r];
         __syncwarp();
       };
-      if (quad && mine) {
-        // the x^2 units of this M tile have smaller unit indices: they are running or done
-        for (uint32_t spin = 0; ld_acquire(a.sq_ready + m) < a.nS; ++spin) {
-          __nanosleep(64);
-          if (spin > (1u << 24)) __trap();
-        }
-        preload(0);
-      }
+      if (quad && mine) preload(0);   // written by the PREP launch
       const long long t_w0 = a.stats ? clock64() : 0;
       mbar_wait(tfull, (uint32_t)it & 1u);
       const long long t_w1 = a.stats ? clock64() : 0;
@@ -532,13 +553,11 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty);
       if (a.stats && threadIdx.x == kEpiThread0) {
-        atomicAdd(a.stats + 5, (unsigned long long)(t_w1 - t_w0));                    // waiting for the accumulators
-        atomicAdd(a.stats + (isS ? 7 : 6), (unsigned long long)(clock64() - t_w1));   // draining them
-        atomicAdd(a.stats + (isS ? 9 : 8), 1ull);
+        atomicAdd(a.stats + (PREP ? 16 : 0) + 5, (unsigned long long)(t_w1 - t_w0));                    // waiting for the accumulators
+        atomicAdd(a.stats + (PREP ? 16 : 0) + 6, (unsigned long long)(clock64() - t_w1));   // draining them
+        atomicAdd(a.stats + (PREP ? 16 : 0) + 8, 1ull);
       }
-      if (isS) __threadfence();   // x^2 sums: visible device-wide before the ready counter moves
       epi_bar();
-      if (isS && et == 0) atomicAdd(a.sq_ready + m, 1);
     }
   }
 
@@ -598,8 +617,8 @@ __global__ void ratspn_prep_leaf_mma_const_kernel(const float* __restrict__ p0, 
 
 }  // namespace
 
-// flags block: redo[Bp/32] | wflag | unit counter | sq_ready[nM]
-static size_t mma_flag_ints(const RatPlan& p) { return (size_t)p.Bp / 32 + 2 + (size_t)ceil_div(p.B, kMmaTileM); }
+// flags block (ints): redo[Bp/32] | wflag | unit counters [2] | pad | debug stats (32 x 8 bytes)
+static size_t mma_flag_ints(const RatPlan& p) { return (size_t)p.Bp / 32 + 4; }
 
 int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st) {
   unsigned char* wimg = reinterpret_cast<unsigned char*>(ws + p.off_wimg);
@@ -635,36 +654,40 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.last_ks = ((p.D + 15) / 16) % 2 == 1 ? 1 : 2;
   a.nM = (int)ceil_div(p.B, kMmaTileM);
   a.mma_mode = env_int("DPK_MMA_MODE", 1);
-  a.look = a.nS > 0 ? std::min(a.nM, env_int("DPK_MMA_LOOKAHEAD", 32)) : 0;
   a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_wimg);
   a.simg = reinterpret_cast<const unsigned char*>(ws + p.off_simg);
+  a.aimg = reinterpret_cast<unsigned char*>(ws + p.off_aimg);
   a.cstm = ws + p.off_cstm;
   a.sq = ws + p.off_sq;
   a.out = ws + p.off_act[0];
   a.redo = reinterpret_cast<int*>(ws + p.off_mflags);
   a.wflag = a.redo + p.Bp / 32;
   a.unit_counter = a.redo + p.Bp / 32 + 1;
-  a.sq_ready = a.redo + p.Bp / 32 + 2;
   a.xlimit = a.quad ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
   const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
-  a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.sq_ready + a.nM + (a.nM & 1)) : nullptr;
-  if (want_stats) DPK_CUDA_TRY(cudaMemsetAsync(a.stats, 0, 16 * 8, st));
-  const int n_units = a.nM * (a.nS + a.nW);
-  const int grid = std::min(std::min(sm_count(), env_int("DPK_MMA_GRID", 1 << 30)), n_units);
+  a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.redo + p.Bp / 32 + 4) : nullptr;
+  if (want_stats) DPK_CUDA_TRY(cudaMemsetAsync(a.stats, 0, 32 * 8, st));
+  const int cap = std::min(sm_count(), env_int("DPK_MMA_GRID", 1 << 30));
+  const int grid_prep = std::min(cap, a.nM * std::max(a.nS, 1)), grid_main = std::min(cap, a.nM * a.nW);
   const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
-  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ratspn_leaf_mma_kernel<<<grid, kThreads, smem, st>>>(a);
-  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel");
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<prep>");
+  ratspn_leaf_mma_kernel<false><<<grid_main, kThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main>");
   if (want_stats) {   // debug only: synchronises
-    unsigned long long h[16];
+    unsigned long long h[32];
     DPK_CUDA_TRY(cudaMemcpyAsync(h, a.stats, sizeof(h), cudaMemcpyDeviceToHost, st));
     DPK_CUDA_TRY(cudaStreamSynchronize(st));
-    const double g = grid;
-    fprintf(stderr, "[mma stats] B=%lld per CTA: mma-warp total %.0f  wait tmem-empty %.0f  wait full %.0f  wait sched %.0f | "
-                    "converter wait empty %.0f | epilogue wait tmem-full %.0f  drain W %.0f (%llu units, %.0f/unit)  "
-                    "drain S %.0f (%llu units)\n", (long long)p.B,
-            h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[8], h[8] ? (double)h[6] / h[8] : 0.0,
-            h[7] / g, h[9]);
+    for (int k = 0; k < 2; ++k) {
+      const unsigned long long* q = h + (k ? 16 : 0);
+      const double g = k ? grid_prep : grid_main;
+      fprintf(stderr, "[mma stats] B=%lld %s per CTA: mma-warp total %.0f  wait tmem-empty %.0f  wait full %.0f  wait sched %.0f | "
+                      "feeder wait empty %.0f | epilogue wait tmem-full %.0f  drain %.0f (%llu units, %.0f/unit)\n",
+              (long long)p.B, k ? "prep" : "main", q[0] / g, q[1] / g, q[2] / g, q[3] / g, q[4] / g, q[5] / g, q[6] / g, q[8],
+              q[8] ? (double)q[6] / q[8] : 0.0);
+    }
   }
   return DPK_OK;
 }

@@ -39,7 +39,7 @@ struct RatPlan {
   // tensor-core leaf (ratspn_leaf_mma.cu): 0 = not used for this call
   int leaf_mma;
   int mma_nS, mma_nW, mma_kb;  // x^2 (region indicator) N tiles, weight N tiles, 32-feature K blocks
-  size_t off_wimg, off_simg, off_cstm, off_sq, off_mflags;
+  size_t off_wimg, off_simg, off_cstm, off_sq, off_mflags, off_aimg;
   int act_regions[DPK_MAX_LEVELS], act_ch[DPK_MAX_LEVELS];
   size_t off_tab, off_cd, off_cst;
   size_t off_wsoft[DPK_MAX_LEVELS], off_wlog[DPK_MAX_LEVELS], w_floats[DPK_MAX_LEVELS];
@@ -150,7 +150,7 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
                    (batch >= kMmaMinBatch || knob == 1) && mma_smem <= (size_t)max_dynamic_smem())
                       ? 1 : 0;
     p->mma_nS = p->mma_nW = p->mma_kb = 0;
-    p->off_wimg = p->off_simg = p->off_cstm = p->off_sq = p->off_mflags = 0;
+    p->off_wimg = p->off_simg = p->off_cstm = p->off_sq = p->off_mflags = p->off_aimg = 0;
     if (p->leaf_mma) {
       p->mma_nS = (p->fwd_kind == kLeafGaussUnit) ? (int)ceil_div(p->G0, kMmaTileN) : 0;
       p->mma_nW = (int)ceil_div((int64_t)p->G0 * p->K, kMmaTileN);
@@ -160,7 +160,8 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
       p->off_simg = take((size_t)p->mma_nS * p->mma_kb * img_floats);   // directly behind wimg (one memset)
       p->off_cstm = take((size_t)p->G0 * p->K);
       p->off_sq = take((size_t)p->G0 * p->Bp);
-      p->off_mflags = take((size_t)p->Bp / 32 + 2 + (size_t)ceil_div(p->B, kMmaTileM) + 1 + 32);  // + debug stats
+      p->off_aimg = take((size_t)ceil_div(p->B, kMmaTileM) * p->mma_kb * 2 * img_floats);   // hi/lo fp16 split of x
+      p->off_mflags = take((size_t)p->Bp / 32 + 4 + 64);   // redo | wflag | unit counters | debug stats
     }
   }
   for (int l = 0; l < p->depth; ++l) {
