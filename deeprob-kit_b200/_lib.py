@@ -80,6 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 c_i32, c_i64, c_u32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t
 
 F_SAVE_ACTIVATIONS = 1
+F_TABLES_VALID = 2
 LEAF_GAUSSIAN, LEAF_BERNOULLI = 0, 1
 
 

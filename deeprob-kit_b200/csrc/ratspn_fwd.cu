@@ -18,14 +18,14 @@ using namespace dpk;
 
 extern "C" size_t dpk_ratspn_workspace_bytes(const dpk_ratspn_desc* desc, int64_t batch, uint32_t flags) {
   RatPlan p;
-  if (make_plan(desc, batch, flags, &p)) return 0;
+  if (make_plan(desc, batch, flags & DPK_F_SAVE_ACTIVATIONS, &p)) return 0;
   return p.total_floats * sizeof(float);
 }
 
 extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,
                                   void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
   RatPlan p;
-  int rc = make_plan(desc, batch, flags, &p);
+  int rc = make_plan(desc, batch, flags & DPK_F_SAVE_ACTIVATIONS, &p);
   if (rc) return rc;
   if (batch == 0) return DPK_OK;
   if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0 || !desc->root_weight ||
@@ -36,7 +36,7 @@ extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, i
   if ((rc = ratspn_check_ws(p, workspace, workspace_bytes))) return rc;
   float* ws = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  {
+  if (!(flags & DPK_F_TABLES_VALID)) {
     ProfScope prof(CAT_PREP, st, 3 + p.n_sum + (p.leaf_mma ? 2 : 0));
     if ((rc = ratspn_run_prep_leaf(desc, p, ws, st))) return rc;
     if ((rc = ratspn_run_prep_weights(desc, p, ws, st))) return rc;

@@ -617,8 +617,9 @@ __global__ void ratspn_prep_leaf_mma_const_kernel(const float* __restrict__ p0, 
 
 }  // namespace
 
-// flags block (ints): redo[Bp/32] | wflag | unit counters [2] | pad | debug stats (32 x 8 bytes)
-static size_t mma_flag_ints(const RatPlan& p) { return (size_t)p.Bp / 32 + 4; }
+// flags block (ints): redo[Bp/32] | unit counters [2] | pad | wflag | debug stats (32 x 8 bytes).
+// redo and the counters are cleared before every pair of launches; wflag belongs to the weight images.
+static size_t mma_call_flag_ints(const RatPlan& p) { return (size_t)p.Bp / 32 + 3; }
 
 int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st) {
   unsigned char* wimg = reinterpret_cast<unsigned char*>(ws + p.off_wimg);
@@ -626,10 +627,10 @@ int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* 
   int* flags = reinterpret_cast<int*>(ws + p.off_mflags);
   // images (wimg, simg are adjacent) and flags are rebuilt every call: parameters change in place
   DPK_CUDA_TRY(cudaMemsetAsync(wimg, 0, (size_t)(p.mma_nW * 2 + p.mma_nS) * p.mma_kb * kImg, st));
-  DPK_CUDA_TRY(cudaMemsetAsync(flags, 0, mma_flag_ints(p) * 4, st));
   const int64_t total = (int64_t)p.G0 * p.K * p.dim;
   const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
-  int* wflag = flags + p.Bp / 32;
+  int* wflag = flags + p.Bp / 32 + 3;
+  DPK_CUDA_TRY(cudaMemsetAsync(wflag, 0, 4, st));
   if (p.fwd_kind == kLeafGaussUnit) {
     ratspn_prep_leaf_mma_kernel<kLeafGaussUnit><<<blocks, 256, 0, st>>>(d->leaf_p0, d->mask, d->region_len, p.G0, p.K,
                                                                          p.dim, p.mma_kb, wimg, simg, wflag);
@@ -661,8 +662,9 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.sq = ws + p.off_sq;
   a.out = ws + p.off_act[0];
   a.redo = reinterpret_cast<int*>(ws + p.off_mflags);
-  a.wflag = a.redo + p.Bp / 32;
-  a.unit_counter = a.redo + p.Bp / 32 + 1;
+  a.unit_counter = a.redo + p.Bp / 32;
+  a.wflag = a.redo + p.Bp / 32 + 3;
+  DPK_CUDA_TRY(cudaMemsetAsync(a.redo, 0, mma_call_flag_ints(p) * 4, st));
   a.xlimit = a.quad ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
   const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
   a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.redo + p.Bp / 32 + 4) : nullptr;

@@ -123,16 +123,19 @@ class _RatSpnLogProb(torch.autograd.Function):
     """log_prob of the whole RAT-SPN: dpk_ratspn_forward / dpk_ratspn_backward."""
 
     @staticmethod
-    def forward(ctx, model, x, *params):
-        need_grad = any(ctx.needs_input_grad)   # False under no_grad / when nothing requires grad
+    def forward(ctx, model_and_mode, x, *params):
+        # needs_input_grad reflects requires_grad of the inputs even when the caller is in no_grad mode (and grad
+        # mode is always off inside forward): the caller's mode is passed in explicitly
+        model, grad_mode = model_and_mode
+        need_grad = grad_mode and any(ctx.needs_input_grad)
         call = model._make_call(x.device)
         batch = x.shape[0]
         flags = _lib.F_SAVE_ACTIVATIONS if need_grad else 0
         out = torch.empty(batch, model.out_classes, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            ws = model._workspace(call, batch, flags, x.device, private=need_grad)
+            ws, extra = model._workspace(call, batch, flags, x.device, private=need_grad)
             rc = _lib.lib().dpk_ratspn_forward(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(ws),
-                                               ws.numel(), flags, _PTR(_lib.stream_ptr(x.device)))
+                                               ws.numel(), flags | extra, _PTR(_lib.stream_ptr(x.device)))
         _lib.check(rc, "dpk_ratspn_forward")
         if need_grad:
             ctx.call, ctx.ws, ctx.model = call, ws, model
@@ -171,7 +174,7 @@ class _RatSpnLogProb(torch.autograd.Function):
 
 def ratspn_log_prob(model, x: torch.Tensor) -> torch.Tensor:
     x = _check_input(x, model.in_features, "RatSpn.forward")
-    return _RatSpnLogProb.apply(model, x, *model._kernel_parameters())
+    return _RatSpnLogProb.apply((model, torch.is_grad_enabled()), x, *model._kernel_parameters())
 
 
 def ratspn_em_statistics(model, x: torch.Tensor):
@@ -197,10 +200,10 @@ def ratspn_em_statistics(model, x: torch.Tensor):
     st.s0, st.s1 = stats["s0"].data_ptr(), stats["s1"].data_ptr()
     st.s2 = stats["s2"].data_ptr() if stats["s2"] is not None else None
     with torch.cuda.device(dev):
-        ws = model._workspace(call, batch, _lib.F_SAVE_ACTIVATIONS, dev, private=False)
+        ws, extra = model._workspace(call, batch, _lib.F_SAVE_ACTIVATIONS, dev, private=False)
         sp = _PTR(_lib.stream_ptr(dev))
         rc = _lib.lib().dpk_ratspn_forward(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(ws), ws.numel(),
-                                           _lib.F_SAVE_ACTIVATIONS, sp)
+                                           _lib.F_SAVE_ACTIVATIONS | extra, sp)
         _lib.check(rc, "dpk_ratspn_forward")
         rc = _lib.lib().dpk_ratspn_em_statistics(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), ctypes.byref(st),
                                                  _ptr(ws), ws.numel(), sp)

@@ -8,6 +8,8 @@ unchanged.  `forward` (= `log_prob`) is ONE autograd node over the fused CUDA pa
 """
 from typing import Optional, Tuple, Type
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -82,6 +84,8 @@ class RatSpn(ProbabilisticModel):
             self.layers.append(layer)
         self.root_layer = RootLayer(groups, nodes, out_classes)
         self._ws_cache = {}
+        self._ws_sig = {}
+        self.cache_tables = True
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _sum_layers(self):
@@ -96,9 +100,15 @@ class RatSpn(ProbabilisticModel):
         return _engine.RatSpnCall(self.base_layer, [layer.weight for layer in self._sum_layers()],
                                   self.root_layer.weight, self.out_classes, self.rg_sum, self.rg_repetitions, device)
 
-    def _workspace(self, call, batch: int, flags: int, device, private: bool) -> torch.Tensor:
+    def _workspace(self, call, batch: int, flags: int, device, private: bool):
+        """(workspace, extra flags).  Inference reuses one grow-only buffer per (device, stream); when neither the
+        buffer nor the parameters (data pointer + version counter, like `unit_scale`) nor the batch size changed
+        since the previous call, the parameter-derived tables inside it are still valid and the kernels that
+        rebuild them are skipped (DPK_F_TABLES_VALID).  In-place updates through autograd-visible ops (optimizers,
+        `load_state_dict`, the constraint modules) bump the version counter; writes through `.data` do not --
+        set `model.cache_tables = False` (or DPK_TABLE_CACHE=0) if you do that."""
         if private:  # activations must survive until backward: one buffer per autograd node
-            return call.workspace(batch, flags, device)
+            return call.workspace(batch, flags, device), 0
         # inference: grow-only buffer per (device, stream), reused call after call (stream-ordered)
         key = (str(device), flags, torch.cuda.current_stream(device).cuda_stream)
         ws = self._ws_cache.get(key)
@@ -106,7 +116,12 @@ class RatSpn(ProbabilisticModel):
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._ws_cache[key] = ws
-        return ws
+            self._ws_sig.pop(key, None)
+        sig = (ws.data_ptr(), batch, call.n_leaf, call.keep[1] is None, os.environ.get("DPK_LEAF_MMA"),
+               tuple((t.data_ptr(), t._version) for t in self._kernel_parameters()))
+        valid = self.cache_tables and os.environ.get("DPK_TABLE_CACHE", "1") != "0" and self._ws_sig.get(key) == sig
+        self._ws_sig[key] = sig
+        return ws, (_engine._lib.F_TABLES_VALID if valid else 0)
 
     # ---- API ---------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:

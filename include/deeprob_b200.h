@@ -36,6 +36,12 @@ extern "C" {
 
 /* flags */
 #define DPK_F_SAVE_ACTIVATIONS 1 /* forward keeps per-level activations in the workspace for backward */
+#define DPK_F_TABLES_VALID 2     /* the parameter-derived tables in `workspace` (leaf tables / operand images, softmax
+                                  * tables) were built by a previous dpk_ratspn_forward with the same descriptor
+                                  * contents, parameter values, batch size and flags: do not rebuild them.  The
+                                  * caller (deeprob_kit_b200.spn._engine) keys this on the parameters' version
+                                  * counters; the reference recomputes log_softmax(weight) on every call
+                                  * (deeprob/spn/layers/ratspn.py:375). */
 
 int dpk_abi_version(void);
 const char* dpk_last_error(void);

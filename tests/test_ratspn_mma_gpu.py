@@ -128,3 +128,29 @@ def test_mma_full_batch_properties(monkeypatch):
     assert rel_err(model(x[perm]), out[perm]) < 1e-6
     monkeypatch.setenv("DPK_LEAF_MMA", "0")
     assert rel_err(model(x[1000:1064]), out[1000:1064]) < 2e-6
+
+
+def test_table_cache_follows_parameter_updates(monkeypatch):
+    """DPK_F_TABLES_VALID: the derived tables are reused only while the parameters' version counters stand still."""
+    cfg = CASES["gauss36"]
+    monkeypatch.setenv("DPK_LEAF_MMA", "1")
+    model = product_model(cfg, DEV, scale_grad=False)
+    x, _ = pg.ratspn_inputs(cfg)
+    xd = x.to(DEV)
+    out0 = model(xd)
+    assert torch.equal(model(xd), out0)                       # second call: cached tables, same bits
+    with torch.no_grad():
+        model.base_layer.loc.add_(0.25)                        # in-place update bumps the version -> rebuild
+        model.root_layer.weight.mul_(0.5)
+    out1 = model(xd)
+    orc, state = oracle_for(cfg)
+    state = dict(state)
+    state["base_layer.loc"] = model.base_layer.loc.detach().cpu().clone()
+    state["root_layer.weight"] = model.root_layer.weight.detach().cpu().clone()
+    ref = orc.load_reference_state(state).double().log_prob(x.double())
+    assert rel_err(out1, ref) < 1e-4
+    assert rel_err(out0, ref) > 1e-3
+    model.cache_tables = False
+    assert torch.equal(model(xd), out1)
+    # a different batch size re-plans the workspace: tables rebuilt, same values row by row
+    assert rel_err(model(xd[:100]), out1[:100]) < 1e-6
