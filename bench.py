@@ -33,7 +33,7 @@ UNIT = "evals/s"
 WORKLOAD = "GaussianRatSpn(784, rg_depth=3, rg_repetitions=16, rg_batch=10, rg_sum=10) log_prob, batch 65536/GPU"
 ALGO_BYTES_PER_SAMPLE = 4 * D + 4 * C          # x row read + LL written
 ALGO_FMA_PER_SAMPLE = 348480                    # one FMA per model parameter
-LEAF_MMA_TRAFFIC = None                         # DRAM bytes per launch of the tcgen05 leaf kernel (ncu), filled in from profiles/
+LEAF_MMA_TRAFFIC = 534.8e6                      # DRAM bytes of one launch of ratspn_leaf_mma_kernel<main> (ncu, profiles/leaf_mma_r1.txt)
 
 
 def parse():
@@ -237,9 +237,9 @@ def run_b200(args, rank, local_rank, world):
     leaf_fma = D * K * REPS                       # x*mu products (the unit-scale expansion; x^2 term is D*REPS more)
     mma = launches.get("ratspn_leaf_mma", 0) > 0
     leaf_cat = "ratspn_leaf_mma" if mma else "ratspn_leaf"
-    leaf_ms = prof_ms[leaf_cat] / args.steps
-    # dominant kernel = the leaf level (one launch per step).  Algorithmic bytes per launch: every sample's
-    # row read once + its LL written once, B samples per launch.
+    leaf_ms = prof_ms[leaf_cat] / args.steps     # the dominant kernel: one launch per step
+    # Algorithmic bytes per launch: every sample's row read once + its LL written once,
+    # B samples per launch.
     algo_gbs = ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -254,23 +254,25 @@ def run_b200(args, rank, local_rank, world):
                 "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * C * 4,
                 "api": "deeprob_kit_b200.spn.streaming.log_prob_host (pinned host in/out, 2-stream chunk pipeline)"},
         "gpu_launches": int(sum(launches.values())),
-        "roofline": {"bound": "hbm", "kernel": "ratspn_leaf_mma_kernel" if mma else "ratspn_leaf_kernel",
+        "roofline": {"bound": "hbm", "kernel": "ratspn_leaf_mma_kernel<main>" if mma else "ratspn_leaf_kernel",
                      "achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65536 (ncu --set full,
-                     # profiles/leaf_mma_r1.txt resp. profiles/leaf_r1.txt): x read once + the leaf activations written
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65536, ncu --set full
+                     # (profiles/leaf_mma_r1.txt resp. profiles/leaf_r1.txt): x images read + leaf activations written
                      "traffic": (LEAF_MMA_TRAFFIC if mma else 490.8e6) if B == 65536 else None,
                      "peak_source": peak_src, "kernel_ms": leaf_ms,
-                     "note": "the path is compute bound (220 flop/B, SURVEY.md 8d): see roofline_tensor / roofline_fp32"},
+                     "note": "the path is compute bound (220 flop/B, SURVEY.md 8d): the binding roofline is roofline_tensor"},
         "kernel_ms_per_step": cats,
     }
     if mma:
-        # dense tensor-core work actually issued: 3 passes x (B x 784 x 1280) + 2 passes x (B x 784 x 128)
-        dense = 2.0 * B * D * (3 * REPS * (1 << DEPTH) * K + 2 * REPS * (1 << DEPTH))
-        line["roofline_tensor"] = {"kernel": "ratspn_leaf_mma_kernel", "issued_tflops": dense / (leaf_ms * 1e-3) / 1e12,
-                                   "peak_tflops": bf16_peak_tf, "frac": dense / (leaf_ms * 1e-3) / 1e12 / bf16_peak_tf,
+        # dense tensor-core work issued by the main GEMM: 3 passes x (B x 784 x 1280)
+        dense = 2.0 * B * D * 3 * REPS * (1 << DEPTH) * K
+        line["roofline_tensor"] = {"bound": "tensor", "kernel": "ratspn_leaf_mma_kernel<main>",
+                                   "achieved": dense / (leaf_ms * 1e-3) / 1e12, "peak": bf16_peak_tf, "unit": "TFLOP/s",
+                                   "frac": dense / (leaf_ms * 1e-3) / 1e12 / bf16_peak_tf,
                                    "useful_tflops": 2.0 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12,
-                                   "note": "issued = dense fp16 MMA flops incl. the zero blocks of the region structure and "
-                                           "the 3-pass split; peak = measured cuBLAS bf16 (sustained)"}
+                                   "peak_source": "measured cuBLAS bf16, sustained (MEASURED_PEAKS.json)",
+                                   "note": "achieved = dense fp16 MMA flops issued, incl. the zero blocks of the region "
+                                           "structure and the 3-pass hi/lo split; ncu: tensor pipe active 66% of elapsed"}
     else:
         line["roofline_fp32"] = {"kernel": "ratspn_leaf_kernel", "achieved_tflops": 4 * leaf_fma * B / (leaf_ms * 1e-3) / 1e12,
                                  "peak_tflops_at_observed_clock": fp32_peak_tf,

@@ -199,7 +199,7 @@ def stream_ptr(device=None) -> int:
 
 PROFILE_CATEGORIES = ["prep", "ratspn_leaf", "ratspn_einsum", "ratspn_root", "ratspn_bwd_einsum", "ratspn_bwd_leaf",
                       "finalize", "layers", "dgcspn_fwd", "dgcspn_bwd", "flow_fwd", "flow_bwd", "gemm",
-                      "ratspn_leaf_mma", "c14", "c15"]
+                      "ratspn_leaf_mma", "ratspn_leaf_mma_prep", "c15"]
 
 
 def profile_enable(on: bool) -> None:

@@ -34,7 +34,7 @@ int max_dynamic_smem();                         // opt-in shared memory per bloc
 // ---- lightweight launch accounting / per-category CUDA-event timing (bench.py, tests) -----------
 enum ProfCat { CAT_PREP = 0, CAT_LEAF = 1, CAT_EINSUM = 2, CAT_ROOT = 3, CAT_BWD_EINSUM = 4, CAT_BWD_LEAF = 5,
                CAT_FINALIZE = 6, CAT_LAYER = 7, CAT_DGC = 8, CAT_DGC_BWD = 9, CAT_FLOW = 10, CAT_FLOW_BWD = 11,
-               CAT_GEMM = 12, CAT_LEAF_MMA = 13, CAT_COUNT = 16 };
+               CAT_GEMM = 12, CAT_LEAF_MMA = 13, CAT_LEAF_MMA_PREP = 14, CAT_COUNT = 16 };
 // RAII: counts `launches` kernel launches in category `cat`; when profiling is enabled also brackets
 // them with CUDA events on `st` (dpk_profile_read sums the elapsed times).
 struct ProfScope {

@@ -475,7 +475,6 @@ int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, 
   a.redo = nullptr;
   if (p.leaf_mma && ((uintptr_t)x & 15) == 0) {
     // tensor-core pass first; the exact kernel below then redoes only the flagged sample groups
-    ProfScope prof(CAT_LEAF_MMA, st);
     int rc = ratspn_run_leaf_mma(p, x, ws, st);
     if (rc) return rc;
     a.redo = reinterpret_cast<const int*>(ws + p.off_mflags);

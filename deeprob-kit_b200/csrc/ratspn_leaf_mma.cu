@@ -674,10 +674,16 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(a);
-  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<prep>");
-  ratspn_leaf_mma_kernel<false><<<grid_main, kThreads, smem, st>>>(a);
-  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main>");
+  {
+    ProfScope prof(CAT_LEAF_MMA_PREP, st);
+    ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(a);
+    DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<prep>");
+  }
+  {
+    ProfScope prof(CAT_LEAF_MMA, st);
+    ratspn_leaf_mma_kernel<false><<<grid_main, kThreads, smem, st>>>(a);
+    DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main>");
+  }
   if (want_stats) {   // debug only: synchronises
     unsigned long long h[32];
     DPK_CUDA_TRY(cudaMemcpyAsync(h, a.stats, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -52,7 +52,8 @@ const char* dpk_last_error(void);
  * `launches` (always) for categories 0..ncat-1 since the previous read, and resets them.
  * Categories: 0 prep, 1 ratspn leaf, 2 ratspn product+sum, 3 ratspn root, 4 ratspn bwd product+sum,
  * 5 ratspn bwd leaf, 6 finalize, 7 stand-alone layers, 8 dgcspn fwd, 9 dgcspn bwd, 10 flow fwd,
- * 11 flow bwd, 12 gemm, 13 ratspn leaf on the tensor cores (tcgen05). */
+ * 11 flow bwd, 12 gemm, 13 ratspn leaf GEMM on the tensor cores (tcgen05),
+ * 14 its operand-preparation launch. */
 #define DPK_PROFILE_CATEGORIES 16
 int dpk_profile_enable(int on);
 int dpk_profile_read(double* ms, int64_t* launches, int32_t ncat);
