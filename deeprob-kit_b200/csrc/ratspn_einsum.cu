@@ -482,6 +482,10 @@ int ratspn_run_prep_weights(const dpk_ratspn_desc* d, const RatPlan& p, float* w
     ratspn_prep_weight_kernel<<<P * p.oc.padded, 128, 0, st>>>(d->sum_weight[e], 0, P, p.O, kin2, p.oc.chunk, p.oc.count,
                                                                 ws + p.off_wsoft[e], ws + p.off_wlog[e]);
     DPK_LAUNCH_CHECK("ratspn_prep_weight_kernel");
+    if (p.einsum_mma[e]) {
+      int rc = ratspn_run_prep_einsum_mma(ws + p.off_wsoft[e], P, p.O, p.act_ch[e], p.oc.chunk, ws + p.off_wmma[e], st);
+      if (rc) return rc;
+    }
   }
   const int kin = p.act_ch[p.depth - 1];
   ratspn_prep_weight_kernel<<<p.cc.padded, 256, 0, st>>>(d->root_weight, 1, p.R, p.C, kin * kin, p.cc.chunk, p.cc.count,
@@ -496,7 +500,9 @@ int ratspn_run_upper(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
     a.in = ws + p.off_act[e]; a.wsoft = ws + p.off_wsoft[e]; a.wlog = ws + p.off_wlog[e];
     a.out = ws + p.off_act[e + 1];
     a.B = p.B; a.Bp = p.Bp; a.P = p.act_regions[e] / 2; a.Kin = p.act_ch[e]; a.O = p.O; a.nOc = p.oc.count;
-    int rc = launch_einsum(a, p.oc.chunk, CAT_EINSUM, st);
+    int rc = p.einsum_mma[e]
+                 ? ratspn_run_einsum_mma(a.in, ws + p.off_wmma[e], a.wsoft, a.wlog, a.out, p.Bp, a.P, a.Kin, a.O, p.oc.chunk, CAT_EINSUM, st)
+                 : launch_einsum(a, p.oc.chunk, CAT_EINSUM, st);
     if (rc) return rc;
   }
   // root = the same contraction with the (globally normalised) root weights, one partial per

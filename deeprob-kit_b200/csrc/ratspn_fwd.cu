@@ -37,7 +37,7 @@ extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, i
   float* ws = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!(flags & DPK_F_TABLES_VALID)) {
-    ProfScope prof(CAT_PREP, st, 3 + p.n_sum + (p.leaf_mma ? 2 : 0));
+    ProfScope prof(CAT_PREP, st, 3 + 2 * p.n_sum + (p.leaf_mma ? 2 : 0));
     if ((rc = ratspn_run_prep_leaf(desc, p, ws, st))) return rc;
     if ((rc = ratspn_run_prep_weights(desc, p, ws, st))) return rc;
   }

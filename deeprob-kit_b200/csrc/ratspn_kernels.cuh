@@ -12,6 +12,12 @@ int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* 
 int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_t st);
 // softmax / log-softmax tables of every sum level and of the root [ratspn_einsum.cu]
 int ratspn_run_prep_weights(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
+// product+sum level with the contraction on the tensor cores                      [ratspn_einsum_mma.cu]
+bool ratspn_einsum_mma_eligible(int Kin, int O, int nOc, int64_t Bp);
+size_t ratspn_einsum_mma_image_floats(int P, int Kin, int O);
+int ratspn_run_prep_einsum_mma(const float* wsoft, int P, int O, int Kin, int OC, float* wimg, cudaStream_t st);
+int ratspn_run_einsum_mma(const float* in, const float* wimg, const float* wsoft, const float* wlog, float* out, int64_t Bp, int P, int Kin,
+                          int O, int OC, int cat, cudaStream_t st);
 // x -> act[0]                                                      [ratspn_leaf.cu]
 int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, float* ws, cudaStream_t st);
 // act[0] -> ... -> out (B, C)                                      [ratspn_einsum.cu]

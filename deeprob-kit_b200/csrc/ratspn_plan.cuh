@@ -43,6 +43,8 @@ struct RatPlan {
   int act_regions[DPK_MAX_LEVELS], act_ch[DPK_MAX_LEVELS];
   size_t off_tab, off_cd, off_cst;
   size_t off_wsoft[DPK_MAX_LEVELS], off_wlog[DPK_MAX_LEVELS], w_floats[DPK_MAX_LEVELS];
+  int einsum_mma[DPK_MAX_LEVELS];      // level uses the tensor-core contraction (ratspn_einsum_mma.cu)
+  size_t off_wmma[DPK_MAX_LEVELS];     // its weight images
   size_t off_rsoft, off_rlog, r_floats;
   size_t off_rtmp;  // [R][C][Bp] per-partition partials of the root
   size_t off_act[DPK_MAX_LEVELS], off_gact[DPK_MAX_LEVELS];
@@ -54,6 +56,10 @@ struct RatPlan {
 };
 
 static inline size_t align64(size_t v) { return (v + 63) / 64 * 64; }
+bool ratspn_einsum_mma_eligible(int Kin, int O, int nOc, int64_t Bp);          // ratspn_einsum_mma.cu
+size_t ratspn_einsum_mma_image_floats(int P, int Kin, int O);
+static inline bool einsum_mma_eligible(int Kin, int O, int nOc, int64_t Bp) { return ratspn_einsum_mma_eligible(Kin, O, nOc, Bp); }
+static inline size_t einsum_mma_image_floats(int P, int Kin, int O) { return ratspn_einsum_mma_image_floats(P, Kin, O); }
 
 constexpr int kLeafMaxStages = 4;  // per-warp ring depth of TMA-bulk parameter chunks (upper bound)
 constexpr int kLeafWarps = 8;
@@ -173,6 +179,8 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     p->w_floats[e] = (size_t)(p->act_regions[e] / 2) * p->oc.count * kin2 * p->oc.chunk;
     p->off_wsoft[e] = take(p->w_floats[e]);
     p->off_wlog[e] = take(p->w_floats[e]);
+    p->einsum_mma[e] = einsum_mma_eligible(p->act_ch[e], p->O, p->oc.count, p->Bp) ? 1 : 0;
+    p->off_wmma[e] = p->einsum_mma[e] ? take(einsum_mma_image_floats(p->act_regions[e] / 2, p->act_ch[e], p->O)) : 0;
   }
   {
     size_t kin2 = (size_t)p->act_ch[p->depth - 1] * p->act_ch[p->depth - 1];

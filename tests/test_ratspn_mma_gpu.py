@@ -154,3 +154,68 @@ def test_table_cache_follows_parameter_updates(monkeypatch):
     assert torch.equal(model(xd), out1)
     # a different batch size re-plans the workspace: tables rebuilt, same values row by row
     assert rel_err(model(xd[:100]), out1[:100]) < 1e-6
+
+
+# ---- product+sum levels with the contraction on the tensor cores (csrc/ratspn_einsum_mma.cu) -----------------
+EINSUM_CASES = {
+    "k10o10": CASES["gauss784"],
+    "k4o3": CASES["gauss_wide"],
+    "k8o8": dict(kind="gaussian", in_features=64, rg_depth=3, rg_repetitions=3, rg_batch=8, rg_sum=8,
+                 out_classes=2, batch=384, nan_frac=0.0, optimize_scale=True),
+    "k16o8": dict(kind="bernoulli", in_features=32, rg_depth=3, rg_repetitions=2, rg_batch=16, rg_sum=8,
+                  out_classes=1, batch=130, nan_frac=0.0, binary=True),
+    "k2o2_nan": dict(kind="gaussian", in_features=40, rg_depth=3, rg_repetitions=4, rg_batch=2, rg_sum=2,
+                     out_classes=3, batch=200, nan_frac=0.3, optimize_scale=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EINSUM_CASES))
+def test_mma_einsum_matches_float64_oracle(name, monkeypatch):
+    cfg = EINSUM_CASES[name]
+    orc = oracle_for(cfg)[0].double()
+    x, g = pg.ratspn_inputs(cfg)
+    ref = orc.log_prob(x.double())
+    outs = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("DPK_EINSUM_MMA", knob)
+        model = product_model(cfg, DEV, scale_grad=False)
+        outs[knob] = model(x.to(DEV)).cpu()
+        assert rel_err(outs[knob], ref) < 1e-4
+    # both contractions agree far inside the north-star tolerance
+    assert rel_err(outs["1"], outs["0"]) < 2e-5
+
+
+def test_mma_einsum_peaked_weights_take_the_exact_path(monkeypatch):
+    """Nearly one-hot mixture weights make the linear-domain sum underflow for most (i, j): exact fallback."""
+    cfg = EINSUM_CASES["k8o8"]
+    monkeypatch.setenv("DPK_EINSUM_MMA", "1")
+    model = product_model(cfg, DEV, scale_grad=False)
+    orc, state = oracle_for(cfg)
+    with torch.no_grad():
+        for layer in model._sum_layers():
+            layer.weight.mul_(40.0)
+    state = dict(state)
+    for k, v in model.state_dict().items():
+        if k.endswith(".weight") and k in state:
+            state[k] = v.detach().cpu().clone()
+    orc = orc.load_reference_state(state).double()
+    x, _ = pg.ratspn_inputs(cfg)
+    assert rel_err(model(x.to(DEV)).cpu(), orc.log_prob(x.double())) < 1e-4
+
+
+def test_mma_einsum_gradients(monkeypatch):
+    cfg = EINSUM_CASES["k10o10"]
+    monkeypatch.setenv("DPK_EINSUM_MMA", "1")
+    monkeypatch.setenv("DPK_LEAF_MMA", "1")
+    model = product_model(cfg, DEV, scale_grad=False)
+    x, g = pg.ratspn_inputs(cfg)
+    with torch.enable_grad():
+        xd = x.to(DEV).requires_grad_(True)
+        out = model(xd)
+        (out * g.to(DEV)).sum().backward()
+    truth = oracle_for(cfg)[0].double().grads(x.double(), g.double(), clean_nan=True)
+    tol = 1e-4 + 4e-7 * float(truth["out"].abs().max())
+    assert norm_err(model.base_layer.loc.grad, truth["loc"].float()) < tol
+    assert norm_err(model.root_layer.weight.grad, truth["root"].float()) < tol
+    for a, b in zip([l.weight.grad for l in model._sum_layers()], truth["sums"]):
+        assert norm_err(a, b.float()) < tol
