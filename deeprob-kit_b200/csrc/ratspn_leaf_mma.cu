@@ -70,6 +70,7 @@ struct LeafMmaArgs {
   int* unit_counter;          // [2] dynamic scheduler of the two launches (zeroed before)
   unsigned char* aimg;        // [nM][KBn][hi | lo][16 KB] fp16 split of x in operand layout, written by the PREP launch
   float xlimit;
+  int linear, relu;           // linear != 0: generic layer, out (B, Ntot) row-major = act(x W^T + bias), cstm = bias
   unsigned long long* stats;  // debug (DPK_MMA_STATS=1): cycles per role spent waiting, else NULL
 };
 
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       if (!isS) {
         const int n = min(col_base + et, a.Ntot - 1);
         const int n_lo = min(col_base + (et & 128), a.Ntot - 1);   // first column of the half `et` belongs to
-        cst_s[et] = __ldg(a.cstm + n);
+        cst_s[et] = a.cstm ? __ldg(a.cstm + n) : 0.f;
         gcol_s[et] = quad ? (n / a.K - n_lo / a.K) * 32 : 0;        // word offset of the column's region in sqw
         g_lo = min(col_base + chalf * 128, a.Ntot - 1) / a.K;
       }
@@ -508,6 +509,26 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
             for (int i = 0; i < 32; ++i) {
               if (i < nvalid && bok) *op = -0.5f * __uint_as_float(v[i]);
               op += a.Bp;
+            }
+          } else if (a.linear) {
+            // generic layer: row-major output, this thread owns 32 consecutive columns of its row
+            if (b < a.B) {
+              float* op = a.out + (size_t)b * a.Ntot + col_base + col0;
+              float r[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                r[i] = __uint_as_float(v[i]) + cst_s[col0 + i];
+                if (a.relu) r[i] = fmaxf(r[i], 0.f);
+              }
+              if (nvalid == 32 && (a.Ntot & 3) == 0) {
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4)
+                  reinterpret_cast<float4*>(op)[i4] = make_float4(r[4 * i4], r[4 * i4 + 1], r[4 * i4 + 2], r[4 * i4 + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < nvalid) op[i] = r[i];
+              }
             }
           } else if (nvalid == 32 && bok && !wide) {
             float* op = a.out + (size_t)(col_base + col0) * a.Bp + b;
@@ -615,6 +636,42 @@ __global__ void ratspn_prep_leaf_mma_const_kernel(const float* __restrict__ p0, 
   cstm[idx] = s;
 }
 
+// ---- generic linear layer on the same kernels ------------------------------------------------------
+// weight images of a dense (N, K) row-major fp32 matrix (nn.Linear.weight): zero padded to 256-row / 32-column tiles
+__global__ void linear_prep_weight_kernel(const float* __restrict__ w, int N, int K, int KBn,
+                                          unsigned char* __restrict__ wimg, int* __restrict__ wflag) {
+  const int64_t total = (int64_t)N * K;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx % K), n = (int)(idx / K);
+    const float v = w[idx];
+    if (!(fabsf(v) <= 60000.f)) *wflag = 1;
+    const uint32_t off = sw64_off((uint32_t)(n & (kMmaTileN - 1)), (uint32_t)(f & 31) >> 3) + (uint32_t)(f & 7) * 2u;
+    unsigned char* img = wimg + ((size_t)(n / kMmaTileN) * KBn + (f >> 5)) * (2 * kImg);
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    *reinterpret_cast<__half*>(img + off) = hi;
+    *reinterpret_cast<__half*>(img + kImg + off) = lo;
+  }
+}
+
+// rows of flagged 32-row groups (non-finite or huge inputs / weights), evaluated exactly in fp32 like F.linear
+__global__ void linear_exact_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                         const float* __restrict__ bias, const int* __restrict__ redo, int64_t B, int K,
+                                         int N, int relu, float* __restrict__ out) {
+  const int64_t grp = blockIdx.x;
+  if (!__ldg(redo + grp)) return;
+  for (int r = 0; r < 32; ++r) {
+    const int64_t b = grp * 32 + r;
+    if (b >= B) break;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = fmaf(x[b * K + k], w[(size_t)n * K + k], s);
+      s += bias ? bias[n] : 0.f;
+      out[b * N + n] = relu ? (s > 0.f || s != s ? s : 0.f) : s;
+    }
+  }
+}
+
 }  // namespace
 
 // flags block (ints): redo[Bp/32] | unit counters [2] | pad | wflag | debug stats (32 x 8 bytes).
@@ -666,6 +723,7 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.wflag = a.redo + p.Bp / 32 + 3;
   DPK_CUDA_TRY(cudaMemsetAsync(a.redo, 0, mma_call_flag_ints(p) * 4, st));
   a.xlimit = a.quad ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
+  a.linear = 0; a.relu = 0;
   const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
   a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.redo + p.Bp / 32 + 4) : nullptr;
   if (want_stats) DPK_CUDA_TRY(cudaMemsetAsync(a.stats, 0, 32 * 8, st));
@@ -700,4 +758,84 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   return DPK_OK;
 }
 
+// ---- generic linear layer --------------------------------------------------------------------------
+struct LinearPlan {
+  int64_t B, Bp;
+  int K, N, nM, nW, KBn;
+  size_t off_aimg, off_wimg, off_flags, total;   // bytes
+};
+static LinearPlan linear_plan(int64_t batch, int K, int N) {
+  LinearPlan p;
+  p.B = batch; p.Bp = round_up(batch > 0 ? batch : 1, 128);
+  p.K = K; p.N = N;
+  p.nM = (int)ceil_div(p.Bp, kMmaTileM); p.nW = (int)ceil_div(N, kMmaTileN); p.KBn = (int)ceil_div(K, kMmaKB);
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (off + n + 255) / 256 * 256; return o; };
+  p.off_aimg = take((size_t)p.nM * p.KBn * 2 * kImg);
+  p.off_wimg = take((size_t)p.nW * p.KBn * 2 * kImg);
+  p.off_flags = take(((size_t)p.Bp / 32 + 4 + 64) * 4);
+  p.total = off;
+  return p;
+}
+
 }  // namespace dpk
+
+using namespace dpk;
+
+extern "C" size_t dpk_linear_workspace_bytes(int64_t batch, int32_t in_features, int32_t out_features) {
+  if (batch < 0 || in_features <= 0 || out_features <= 0) return 0;
+  return linear_plan(batch, in_features, out_features).total;
+}
+
+extern "C" int dpk_linear_forward(const float* x, const float* weight, const float* bias, int64_t batch,
+                                  int32_t in_features, int32_t out_features, int32_t relu, float* out, void* workspace,
+                                  size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (batch < 0 || in_features <= 0 || out_features <= 0) return set_error(DPK_E_ARG, "linear: bad shape");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !out) return set_error(DPK_E_ARG, "null pointer argument");
+  if (in_features % 4 || ((uintptr_t)x & 15) || ((uintptr_t)out & 15))
+    return set_error(DPK_E_ARG, "linear: in_features must be a multiple of 4 and x / out 16-byte aligned");
+  const LinearPlan p = linear_plan(batch, in_features, out_features);
+  if (!workspace || ((uintptr_t)workspace & 255)) return set_error(DPK_E_WORKSPACE, "workspace must be 256-byte aligned");
+  if (workspace_bytes < p.total) return set_error(DPK_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, p.total);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* flg = reinterpret_cast<int*>(ws + p.off_flags);
+  LeafMmaArgs a;
+  a.x = x; a.B = p.B; a.Bp = p.Bp; a.D = in_features;
+  a.quad = 0; a.G0 = 0; a.K = 1; a.Ntot = out_features;
+  a.nS = 0; a.nW = p.nW; a.KBn = p.KBn;
+  a.last_ks = ((in_features + 15) / 16) % 2 == 1 ? 1 : 2;
+  a.nM = (int)ceil_div(p.B, kMmaTileM);
+  a.mma_mode = env_int("DPK_MMA_MODE", 1);
+  a.wimg = ws + p.off_wimg; a.simg = nullptr; a.aimg = ws + p.off_aimg;
+  a.cstm = bias; a.sq = nullptr; a.out = out;
+  a.redo = flg; a.unit_counter = flg + p.Bp / 32; a.wflag = flg + p.Bp / 32 + 3;
+  a.xlimit = 60000.f; a.linear = 1; a.relu = relu ? 1 : 0; a.stats = nullptr;
+  if (!(flags & DPK_F_TABLES_VALID)) {
+    ProfScope prof(CAT_PREP, st, 1);
+    DPK_CUDA_TRY(cudaMemsetAsync(ws + p.off_wimg, 0, (size_t)p.nW * p.KBn * 2 * kImg, st));
+    DPK_CUDA_TRY(cudaMemsetAsync(flg + p.Bp / 32 + 3, 0, 4, st));
+    const int64_t total = (int64_t)out_features * in_features;
+    linear_prep_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 8192), 256, 0, st>>>(
+        weight, out_features, in_features, p.KBn, ws + p.off_wimg, flg + p.Bp / 32 + 3);
+    DPK_LAUNCH_CHECK("linear_prep_weight_kernel");
+  }
+  DPK_CUDA_TRY(cudaMemsetAsync(flg, 0, ((size_t)p.Bp / 32 + 3) * 4, st));
+  const int cap = sm_count();
+  const int grid_prep = std::min(cap, a.nM), grid_main = std::min(cap, a.nM * a.nW);
+  const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof(CAT_GEMM, st, 3);
+    ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(a);
+    DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<prep> (linear)");
+    ratspn_leaf_mma_kernel<false><<<grid_main, kThreads, smem, st>>>(a);
+    DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main> (linear)");
+    linear_exact_rows_kernel<<<(unsigned)(p.Bp / 32), 256, 0, st>>>(x, weight, bias, flg, p.B, in_features, out_features,
+                                                                      relu ? 1 : 0, out);
+    DPK_LAUNCH_CHECK("linear_exact_rows_kernel");
+  }
+  return DPK_OK;
+}

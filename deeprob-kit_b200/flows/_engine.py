@@ -233,3 +233,67 @@ class _NormalPrior(torch.autograd.Function):
 
 def normal_prior(z, ildj, loc, scale):
     return _NormalPrior.apply(z, ildj, loc, scale)
+
+
+# ---- conditioner MLP on the tensor cores (inference) ---------------------------------------------------------
+MLP_MIN_BATCH = 2048
+
+
+def linear(x, weight, bias, relu, cache=None):
+    """act(x @ weight.T + bias) through dpk_linear_forward (tcgen05 GEMM, fp32-accurate 3-pass fp16 operands).
+    `cache`: dict owned by the calling layer -- workspace + weight signature, so the weight images are rebuilt only
+    when the weight changed (data pointer / version counter, like RatSpn._workspace)."""
+    import ctypes
+    import os
+    from .. import _lib
+    x = x.contiguous()
+    batch, k = x.shape
+    n = weight.shape[0]
+    out = torch.empty(batch, n, dtype=torch.float32, device=x.device)
+    nbytes = _lib.lib().dpk_linear_workspace_bytes(batch, k, n)
+    cache = cache if cache is not None else {}
+    key = (str(x.device), torch.cuda.current_stream(x.device).cuda_stream)
+    ws = cache.get(key)
+    if ws is None or ws[0].numel() < nbytes:
+        ws = [torch.empty(nbytes, dtype=torch.uint8, device=x.device), None]
+        cache[key] = ws
+    sig = (batch, weight.data_ptr(), weight._version)
+    flags = _lib.F_TABLES_VALID if (ws[1] == sig and os.environ.get("DPK_TABLE_CACHE", "1") != "0") else 0
+    ws[1] = sig
+    w = weight.detach()
+    b = bias.detach() if bias is not None else None
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dpk_linear_forward(
+            ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+            ctypes.c_void_p(b.data_ptr() if b is not None else 0), batch, k, n, 1 if relu else 0,
+            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws[0].data_ptr()), ws[0].numel(), flags,
+            ctypes.c_void_p(_lib.stream_ptr(x.device)))
+    _lib.check(rc, "dpk_linear_forward")
+    return out
+
+
+def mlp(network, x):
+    """Evaluate an nn.Sequential of Linear / ReLU layers (the conditioner of CouplingLayer1d,
+    deeprob/flows/layers/coupling.py:45-56).  Inference on a large CUDA batch goes through `linear`; training (any
+    gradient needed), small batches and unusual layer stacks use the stock modules (cuBLAS)."""
+    import os
+    from torch import nn
+    mods = list(network)
+    ok = (not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+          and x.shape[0] >= MLP_MIN_BATCH and os.environ.get("DPK_LINEAR_MMA", "1") != "0")
+    plan = []
+    i = 0
+    while ok and i < len(mods):
+        m = mods[i]
+        if type(m) is not nn.Linear or m.in_features % 4 or m.weight.dtype != torch.float32 or not m.weight.is_contiguous():
+            ok = False
+            break
+        relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+        plan.append((m, relu))
+        i += 2 if relu else 1
+    if not ok:
+        return network(x)
+    for m, relu in plan:
+        cache = m.__dict__.setdefault("_dpk_linear_cache", {})
+        x = linear(x, m.weight, m.bias, relu, cache)
+    return x

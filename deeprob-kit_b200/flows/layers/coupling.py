@@ -1,6 +1,7 @@
 """RealNVP / NICE coupling layers (interface of deeprob/flows/layers/coupling.py: CouplingLayer1d :15-104,
-CouplingLayer2d :107-272, CouplingBlock2d :275-408).  The conditioner network is evaluated by library
-GEMMs/convolutions; everything after it -- chunk, ScaledTanh, masking, affine transform, per-sample
+CouplingLayer2d :107-272, CouplingBlock2d :275-408).  The 1-D conditioner MLP is evaluated by the tcgen05 GEMM of
+csrc/ratspn_leaf_mma.cu in inference (dpk_linear_forward) and by library GEMMs when gradients are needed; the 2-D
+conditioners are library convolutions; everything after it -- chunk, ScaledTanh, masking, affine transform, per-sample
 log-det reduction -- is ONE kernel (csrc/flows.cu: dpk_coupling_forward/backward)."""
 from typing import Tuple
 
@@ -39,7 +40,7 @@ class CouplingLayer1d(Bijector):
         return mask, 1.0 - mask
 
     def _transform(self, x, direction):
-        z = self.network(self.mask * x)
+        z = _engine.mlp(self.network, self.mask * x)
         w = self.scale_act.weight if self.affine else None
         out, ldj = _engine.coupling(x, z, w, self.inv_mask, self.in_features, 0, self.affine, direction, 1)
         return out, (ldj if self.affine else 0.0)

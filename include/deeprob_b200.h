@@ -231,6 +231,18 @@ int dpk_normal_prior_forward(const float* z, const float* loc, const float* scal
 int dpk_normal_prior_backward(const float* z, const float* loc, const float* scale, const float* grad_out,
                               float* grad_z, int64_t batch, int32_t features, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense layer of the coupling / autoregressive conditioners (nn.Linear in deeprob/flows/layers/coupling.py:45-56,
+ * MaskedLinear deeprob/torch/utils.py:73-96 with weight * mask folded by the caller):
+ *   out (B, out_features) = act(x (B, in_features) @ weight (out_features, in_features)^T + bias), act = ReLU or none,
+ * as a tcgen05 GEMM with fp32-accurate 3-pass hi/lo fp16 operands (the kernels of the RAT-SPN leaf level); rows with
+ * non-finite or |x| > 6e4 inputs are re-evaluated exactly in fp32.  Inference only (no backward entry point).
+ * in_features % 4 == 0; x, out 16-byte aligned; `flags` may carry DPK_F_TABLES_VALID (weight images still valid). */
+size_t dpk_linear_workspace_bytes(int64_t batch, int32_t in_features, int32_t out_features);
+int dpk_linear_forward(const float* x, const float* weight, const float* bias /* may be NULL */, int64_t batch,
+                       int32_t in_features, int32_t out_features, int32_t relu, float* out, void* workspace,
+                       size_t workspace_bytes, uint32_t flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
