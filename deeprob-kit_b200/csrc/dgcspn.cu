@@ -352,6 +352,109 @@ __global__ void __launch_bounds__(128) dgc_sum_fwd_smem_kernel(const float* __re
   }
 }
 
+// Fused depthwise SpatialProductLayer + SpatialSumLayer (inference): the product output -- the largest tensor of
+// the model, written once and read once by the unfused pair -- never touches HBM.  thread = output pixel; the four
+// taps of every input channel are gathered straight from the product layer's input (lanes = consecutive pixels:
+// row-wise coalesced; the 2x2 neighbourhoods overlap between lanes and rows, so most taps hit L1/L2), the IC
+// product values of NB samples stay in registers for the max pass, the mixture pass and the exact fallback.
+template <int IC> struct PsNB { static constexpr int value = IC <= 8 ? 4 : 2; };   // samples a thread carries at once
+template <int IC, int OC>
+__global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wsoft,
+                                                              const float* __restrict__ wlog, float* __restrict__ out,
+                                                              int64_t B, int O, ProdDesc d, int64_t per_slice) {
+  extern __shared__ float wsm[];  // [IC][OC][128]
+  constexpr int kPsNB = PsNB<IC>::value;
+  const int lane_px = threadIdx.x;
+  const int HW = d.OH * d.OW, IHW = d.H * d.W;
+  const int hw = blockIdx.x * 128 + lane_px;
+  const bool live = hw < HW;
+  const int oh = live ? hw / d.OW : 0, ow = live ? hw - (hw / d.OW) * d.OW : 0;
+  int off[4];
+  bool ok[4];
+#pragma unroll
+  for (int tap = 0; tap < 4; ++tap) {
+    const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top;
+    const int xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
+    ok[tap] = live && y >= 0 && y < d.H && xx >= 0 && xx < d.W;
+    off[tap] = ok[tap] ? y * d.W + xx : 0;
+  }
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  for (int o0 = 0; o0 < O; o0 += OC) {
+    __syncthreads();
+    for (int i = 0; i < IC; ++i)
+#pragma unroll
+      for (int o = 0; o < OC; ++o)
+        wsm[(i * OC + o) * 128 + lane_px] = (live && o0 + o < O) ? __ldg(wsoft + ((size_t)(o0 + o) * IC + i) * HW + hw) : 0.f;
+    __syncthreads();
+    if (!live) continue;
+    for (int64_t bb = b0; bb < b1; bb += kPsNB) {
+      float pv[kPsNB][IC], m[kPsNB];
+#pragma unroll
+      for (int s = 0; s < kPsNB; ++s) {
+        const float* xb = x + (size_t)min((long long)(bb + s), (long long)(b1 - 1)) * IC * IHW;   // clamped: loads unconditional
+#pragma unroll
+        for (int i = 0; i < IC; ++i) {
+          const float* xc = xb + (size_t)i * IHW;
+          float v = 0.f;                         // zero padding = log 1
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap)
+            if (ok[tap]) v += xc[off[tap]];
+          pv[s][i] = v;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < kPsNB; ++s) {
+        float mm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < IC; ++i) mm = fmaxf(mm, pv[s][i]);
+        m[s] = (fabsf(mm) <= FLT_MAX) ? mm : 0.f;   // all -inf / non-finite: the exact path sorts it out
+      }
+      float acc[kPsNB][OC];
+#pragma unroll
+      for (int s = 0; s < kPsNB; ++s)
+#pragma unroll
+        for (int o = 0; o < OC; ++o) acc[s][o] = 0.f;
+#pragma unroll
+      for (int i = 0; i < IC; ++i) {
+        float w[OC];
+#pragma unroll
+        for (int o = 0; o < OC; ++o) w[o] = wsm[(i * OC + o) * 128 + lane_px];
+#pragma unroll
+        for (int s = 0; s < kPsNB; ++s) {
+          const float e = __expf(pv[s][i] - m[s]);
+#pragma unroll
+          for (int o = 0; o < OC; ++o) acc[s][o] = fmaf(w[o], e, acc[s][o]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < kPsNB; ++s) {
+        if (bb + s >= b1) continue;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+          if (o0 + o >= O) continue;
+          float y;
+          if (acc[s][o] >= 1e-18f && acc[s][o] <= FLT_MAX) {
+            y = m[s] + __logf(acc[s][o]);
+          } else {  // exact log-domain evaluation
+            float mm = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < IC; ++i) mm = fmaxf(mm, pv[s][i] + wlog[((size_t)(o0 + o) * IC + i) * HW + hw]);
+            if (!(fabsf(mm) <= FLT_MAX)) {
+              y = mm;
+            } else {
+              float ss = 0.f;
+#pragma unroll
+              for (int i = 0; i < IC; ++i) ss += expf(pv[s][i] + wlog[((size_t)(o0 + o) * IC + i) * HW + hw] - mm);
+              y = mm + logf(ss);
+            }
+          }
+          out[((bb + s) * O + o0 + o) * HW + hw] = y;
+        }
+      }
+    }
+  }
+}
+
 // Backward: posterior of input i under output o is w[o,i]*exp(x_i - y_o).
 //   gx[b,i]    = sum_o g[b,o] * w[o,i] * exp(x_i - y_o)
 //   N[o,i,hw] += sum_b g[b,o] * w[o,i] * exp(x_i - y_o)       (then grad_raw = N - softmax * sum_i N)
@@ -665,6 +768,52 @@ extern "C" int dpk_dgc_sum_forward(const float* x, const float* weight, int64_t 
     }
   }
   DPK_LAUNCH_CHECK("dgc_sum_fwd_kernel");
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const float* x, const float* weight,
+                                       int64_t batch, int32_t out_channels, float* out, float* scratch, void* stream) {
+  if (!desc || batch < 0 || out_channels <= 0) return set_error(DPK_E_ARG, "dgc_prodsum: bad arguments");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !out || !scratch) return set_error(DPK_E_ARG, "dgc_prodsum: null pointer");
+  const ProdDesc d = to_prod(desc);
+  const int I = d.OC, hw = d.OH * d.OW;
+  if (!d.depthwise || d.C != d.OC || !(I == 2 || I == 4 || I == 8 || I == 16) || d.sh <= 0 || d.sw <= 0)
+    return set_error(DPK_E_ARG, "dgc_prodsum: only depthwise products with 2, 4, 8 or 16 channels are fused");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nw = (size_t)out_channels * I * hw;
+  float* wsoft = scratch;
+  float* wlog = scratch + nw;
+  ProfScope prof(CAT_DGC, st, 2);
+  dgc_sum_prep_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(weight, wsoft, wlog, out_channels, I, hw);
+  DPK_LAUNCH_CHECK("dgc_sum_prep_kernel");
+  const int64_t bx = ceil_div(hw, 128);
+  const int OC = out_channels <= 2 ? 2 : (out_channels <= 4 ? 4 : 8);
+  const size_t smem = (size_t)I * OC * 128 * sizeof(float);
+  const int64_t per = round_up(ceil_div(batch, std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)env_int_dgc("DPK_DGC_CTAS_PER_SM", 8) * sm_count(), bx)),
+                                                                   std::max<int64_t>(1, batch / 64))), 4);
+  dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
+#define DPK_PS(ic_, oc_)                                                                                            \
+  {                                                                                                                 \
+    auto kern = dgc_prodsum_fwd_kernel<ic_, oc_>;                                                                   \
+    if (smem > 48 * 1024) DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, 128, smem, st>>>(x, wsoft, wlog, out, batch, out_channels, d, per);                                \
+  }
+#define DPK_PS_IC(ic_)                                    \
+  switch (OC) {                                           \
+    case 2: DPK_PS(ic_, 2) break;                         \
+    case 4: DPK_PS(ic_, 4) break;                         \
+    default: DPK_PS(ic_, 8) break;                        \
+  }
+  switch (I) {
+    case 2: DPK_PS_IC(2) break;
+    case 4: DPK_PS_IC(4) break;
+    case 8: DPK_PS_IC(8) break;
+    default: DPK_PS_IC(16) break;
+  }
+#undef DPK_PS_IC
+#undef DPK_PS
+  DPK_LAUNCH_CHECK("dgc_prodsum_fwd_kernel");
   return DPK_OK;
 }
 

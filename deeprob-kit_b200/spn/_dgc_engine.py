@@ -152,3 +152,26 @@ def mixture(x, weight):
 def root(x, weight):
     _lib.require_cuda(x, "SpatialRootLayer.forward")
     return _Root.apply(x, weight)
+
+
+def product_mixture(x, desc, weight):
+    """Inference fusion of a depthwise SpatialProductLayer and the SpatialSumLayer behind it
+    (dpk_dgc_prodsum_forward): the product output is never materialised.  No autograd node: callers use it only
+    when no gradient is needed."""
+    x, weight = _check4d(x, "SpatialProductLayer.forward"), _f32c(weight.detach())
+    b = x.shape[0]
+    cout = weight.shape[0]
+    out = torch.empty(b, cout, desc.out_height, desc.out_width, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(2 * weight.numel(), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dpk_dgc_prodsum_forward(ctypes.byref(desc), _ptr(x), _ptr(weight), b, cout, _ptr(out),
+                                                _ptr(scratch), _stream(x.device))
+    _lib.check(rc, "dpk_dgc_prodsum_forward")
+    return out
+
+
+def can_fuse_product_mixture(prod_layer, sum_layer) -> bool:
+    d = prod_layer._desc
+    return (bool(d.depthwise) and d.channels == d.out_channels and d.channels in (2, 4, 8, 16)
+            and tuple(sum_layer.weight.shape[1:]) == (d.out_channels, d.out_height, d.out_width)
+            and d.channels * min(8, max(2, sum_layer.weight.shape[0])) * 512 <= 96 * 1024)

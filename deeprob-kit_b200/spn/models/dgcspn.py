@@ -3,12 +3,15 @@ layer schedule (:100-125) and state_dict keys; layers run on csrc/dgcspn.cu."""
 from typing import List, Optional, Tuple, Union
 
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import autograd
 
 from ...torch.base import ProbabilisticModel
 from ...torch.constraints import ScaleClipper
+from .. import _dgc_engine
 from ..layers.dgcspn import SpatialGaussianLayer, SpatialProductLayer, SpatialRootLayer, SpatialSumLayer
 
 
@@ -93,8 +96,22 @@ class DgcSpn(ProbabilisticModel):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Log-likelihood (B, out_classes) of x (B, C, H, W); NaN = marginalised variable."""
         h = self.base_layer(x)
-        for layer in self.layers:
-            h = layer(h)
+        layers = list(self.layers)
+        # inference: a depthwise product layer and the sum layer behind it run as one kernel (its output, the
+        # largest tensor of the model, is never written); with gradients every layer stays its own autograd node
+        fuse = not torch.is_grad_enabled() and os.environ.get("DPK_DGC_FUSE", "1") != "0"
+        i = 0
+        while i < len(layers):
+            layer = layers[i]
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            if (fuse and isinstance(layer, SpatialProductLayer) and isinstance(nxt, SpatialSumLayer)
+                    and not (nxt.training and nxt.dropout is not None)
+                    and _dgc_engine.can_fuse_product_mixture(layer, nxt)):
+                h = _dgc_engine.product_mixture(h, layer._desc, nxt.weight)
+                i += 2
+            else:
+                h = layer(h)
+                i += 1
         return self.root_layer(h)
 
     def mpe(self, x: torch.Tensor) -> torch.Tensor:

@@ -171,6 +171,12 @@ int dpk_dgc_sum_backward(const float* x, const float* weight, const float* out, 
                          int64_t batch, int32_t in_channels, int32_t out_channels, int32_t hw, float* grad_x,
                          float* grad_weight, float* scratch, void* stream);
 
+/* Inference fusion of a depthwise SpatialProductLayer (dgcspn.py:224-236) with the SpatialSumLayer that follows it
+ * (dgcspn.py:289-304): x (B,C,H,W) -> out (B,Cout,OH,OW) without materialising the product output.
+ * weight (Cout, C, OH, OW) raw logits; scratch: 2*Cout*C*OH*OW floats.  C in {2,4,8,16}; other shapes: DPK_E_ARG. */
+int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const float* x, const float* weight, int64_t batch,
+                            int32_t out_channels, float* out, float* scratch, void* stream);
+
 /* SpatialRootLayer.forward (dgcspn.py:343-355): x (B, Q = C*H*W), weight (classes, Q) -> out (B, classes).
  * scratch: classes*Q floats (forward), 2*classes*Q floats (backward). */
 int dpk_dgc_root_forward(const float* x, const float* weight, int64_t batch, int64_t features,

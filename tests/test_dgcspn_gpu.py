@@ -93,3 +93,17 @@ def test_config3_batch_properties():
     idx = torch.arange(0, 1030, 41)
     assert rel_err(out[idx.to(DEV)].cpu(), orc.log_prob(x[idx])) < TOL
     assert float(model(torch.full((3, 1, 28, 28), float("nan"), device=DEV)).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["dw8", "mnist", "mnist_pool", "mixed16"])
+def test_fused_product_sum_matches_layerwise(name, monkeypatch):
+    """Inference fuses every depthwise product layer with the sum layer behind it (dpk_dgc_prodsum_forward):
+    same values as the layer-by-layer path, NaN (marginalised) inputs included."""
+    cfg = pg.DGCSPN_CASES[name]
+    model = dgc_product_model(cfg, DEV)
+    x = pg.dgcspn_inputs(cfg)[0].to(DEV)
+    monkeypatch.setenv("DPK_DGC_FUSE", "1")
+    fused = model(x)
+    monkeypatch.setenv("DPK_DGC_FUSE", "0")
+    plain = model(x)
+    assert rel_err(fused, plain) < 2e-6
