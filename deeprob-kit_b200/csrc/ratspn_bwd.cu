@@ -13,7 +13,7 @@
 //   gradients w.r.t. loc/scale/logits are closed forms of them)
 #include <algorithm>
 
-#include "ratspn_plan.cuh"
+#include "ratspn_kernels.cuh"
 
 namespace dpk {
 
@@ -233,6 +233,7 @@ struct LeafBwdArgs {
   float* s1; float* s2; float* snan; float* s0tot;
   int64_t B, Bp, samples_per_cta;
   int D, G0, K, dim, TS, nKc;
+  const int* only_if;   // NULL, or device flag: the kernel runs only when it is != 0 (fallback behind the GEMM path)
 };
 
 template <int KC> struct LeafBwdJD { static constexpr int value = (KC <= 10) ? 4 : 2; };
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(256) ratspn_leaf_bwd_stats_kernel(const LeafBw
   constexpr int JD = LeafBwdJD<KC>::value;
   constexpr int KS = (KC + 3) / 4 * 4;
   constexpr bool GAUSS = (KIND == DPK_LEAF_GAUSSIAN);
+  if (a.only_if && !__ldg(a.only_if)) return;
   const int TS = a.TS;
   float* gs = sm;                         // [8][TS][KS]  (first: rows must stay 16-byte aligned)
   float* xs = gs + (size_t)8 * TS * KS;   // [TS][D]
@@ -604,7 +606,12 @@ static int run_backward(const dpk_ratspn_desc* d, const RatPlan& p, const float*
     a.x = x; a.mask = d->mask; a.region_len = d->region_len; a.g0 = ws + p.off_gact[0];
     a.s1 = ws + p.off_s1; a.s2 = ws + p.off_s2; a.snan = ws + p.off_snan; a.s0tot = ws + p.off_s0tot;
     a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
-    a.TS = 0; a.samples_per_cta = 0;
+    a.TS = 0; a.samples_per_cta = 0; a.only_if = nullptr;
+    if (p.stats_mma && ((uintptr_t)a.g0 & 15) == 0) {
+      ProfScope prof(CAT_BWD_LEAF, st, 6);
+      int rc2 = ratspn_run_leaf_stats_mma(d, p, x, a.g0, ws, a.s1, a.s2, a.s0tot, &a.only_if, st);
+      if (rc2) return rc2;
+    }
     int rc = (p.kind == DPK_LEAF_GAUSSIAN) ? launch_leaf_stats<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, st)
                                            : launch_leaf_stats<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, st);
     if (rc) return rc;

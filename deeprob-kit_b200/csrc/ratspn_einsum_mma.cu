@@ -37,7 +37,7 @@ constexpr float kScaleA = 16384.f;        // 2^14
 constexpr float kScaleB = 32768.f;        // 2^15
 constexpr float kLogScale = 29.f * 0.693147180559945309417f;   // log(2^29)
 constexpr float kMinSum = 1e-5f * 536870912.f;                 // 1e-5 in the scaled domain
-constexpr uint32_t kEmSpinLimit = 1u << 22;
+constexpr uint32_t kEmSpinLimit = 1u << 26;
 
 struct EinsumMmaArgs {
   const float* in;             // [2P][Kin][Bp]

@@ -10,6 +10,10 @@ int ratspn_run_prep_leaf(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, 
 // tensor-core leaf: weight images / constants, and x -> act[0] for every clean 32-sample group (flags the rest)
 int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
 int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_t st);
+// leaf moments S0/S1/S2 of the backward as a tcgen05 GEMM over the batch; *fallback = device flag (!= 0: inputs
+// outside the fast path's range, the caller's exact kernel must run)                [ratspn_leaf_mma.cu]
+int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, const float* g0, float* ws,
+                              float* s1, float* s2, float* s0tot, const int** fallback, cudaStream_t st);
 // softmax / log-softmax tables of every sum level and of the root [ratspn_einsum.cu]
 int ratspn_run_prep_weights(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
 // product+sum level with the contraction on the tensor cores                      [ratspn_einsum_mma.cu]

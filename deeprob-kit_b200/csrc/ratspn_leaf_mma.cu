@@ -52,7 +52,7 @@ constexpr int kImg = kMmaTileN * kMmaKB * 2;  // 16 KB: [256 rows][64 B] fp16, 6
 constexpr int kStage = 4 * kImg;              // A hi | A lo | B hi | B lo
 constexpr int kThreads = 576;
 constexpr int kEpiThread0 = 320;              // first epilogue thread (warp 10)
-constexpr uint32_t kSpinLimit = 1u << 22;     // bounded waits: a broken pipeline traps instead of hanging
+constexpr uint32_t kSpinLimit = 1u << 26;     // bounded waits (seconds): a broken pipeline traps instead of hanging
 
 struct LeafMmaArgs {
   const float* x;
@@ -70,7 +70,10 @@ struct LeafMmaArgs {
   int* unit_counter;          // [2] dynamic scheduler of the two launches (zeroed before)
   unsigned char* aimg;        // [nM][KBn][hi | lo][16 KB] fp16 split of x in operand layout, written by the PREP launch
   float xlimit;
-  int linear, relu;           // linear != 0: generic layer, out (B, Ntot) row-major = act(x W^T + bias), cstm = bias
+  int64_t lda;                // row stride of x (elements); columns >= D read as 0
+  int nC, kchunk;             // split-K: nC chunks of kchunk K blocks (nC == 1: the whole K range per unit)
+  float ascale, oscale;       // PREP multiplies the A operand by ascale; linear == 2 multiplies the result by oscale
+  int linear, relu;           // linear == 2: out (B, Ntot) += result (atomic, split-K partial sums); linear != 0: generic layer, out (B, Ntot) row-major = act(x W^T + bias), cstm = bias
   unsigned long long* stats;  // debug (DPK_MMA_STATS=1): cycles per role spent waiting, else NULL
 };
 
@@ -203,14 +206,17 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   const uint32_t tmem = *tmem_slot;
 
   // units of this launch: (M tile m, N tile j), M-tile-major
+  // split-K (nC > 1): chunk-major order, so that the operand images of one K chunk are shared through L2 by all
+  // units of the chunk; the chunk index travels in the upper half of j
   const int upm = PREP ? max(a.nS, 1) : a.nW;
-  const int n_units = a.nM * upm;
+  const int n_units = a.nM * upm * a.nC;
   // every role walks the same unit sequence: entry `it` of the scheduler ring
   auto next_unit = [&](int it, int* m, int* j) -> bool {
     mbar_wait(sfull + (it & (kSchedSlots - 1)), (uint32_t)(it / kSchedSlots) & 1u);
     const int u = sched_s[it & (kSchedSlots - 1)];
     if (u < 0) return false;
-    *m = u / upm; *j = u - *m * upm;
+    const int c = u / (a.nM * upm), r = u - c * (a.nM * upm);
+    *m = r / upm; *j = (r - *m * upm) | (c << 16);
     return true;
   };
   int m, j;
@@ -229,10 +235,12 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u < 0) break;
       if (!tensor) continue;
-      m = u / upm; j = u - m * upm;
+      const int c = u / (a.nM * upm), r = u - c * (a.nM * upm);
+      m = r / upm; j = r - m * upm;
+      const int kb0 = c * a.kchunk, kb1 = min(a.KBn, kb0 + a.kchunk);
       const unsigned char* src = PREP ? a.simg + (size_t)j * a.KBn * kImg : a.wimg + (size_t)j * a.KBn * (2 * kImg);
       const uint32_t bytes = PREP ? kImg : 2 * kImg;
-      for (int kb = 0; kb < a.KBn; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (lane == 0) {
           mbar_wait(empty + stage, phase ^ 1u);
           mbar_expect_tx(full + stage, bytes);
@@ -252,6 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       if (!next_unit(it, &m, &j)) break;
       if (a.stats) w_sched += clock64() - t0;
       if (!tensor) continue;
+      const int kb0 = (j >> 16) * a.kchunk, kb1 = min(a.KBn, kb0 + a.kchunk);
+      j &= 0xffff;
       const int cols = (PREP ? a.G0 : a.Ntot) - j * kMmaTileN;
       const int N = min(kMmaTileN, (cols + 15) / 16 * 16);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);  // fp32 accum, fp16 A/B, K-major, M=128
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       tc_fence_after();
       // weight-stationary issue needs N in {64, 128, 256}
       const bool ws = a.mma_mode == 1 && (N == 64 || N == 128 || N == 256);
-      for (int kb = 0; kb < a.KBn; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         t0 = a.stats ? clock64() : 0;
         mbar_wait(full + stage, phase);          // whole warp: keeps everything below warp-uniform
         if (a.stats) w_full += clock64() - t0;
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
               const uint32_t a_hi0 = lo0 + 2 * ks, a_hi1 = a_hi0 + (kImg / 32);
               const uint32_t a_lo0 = a_hi0 + (kImg / 16), a_lo1 = a_lo0 + (kImg / 32);
               const uint32_t b_hi = a_hi0 + 2 * (kImg / 16), b_lo = a_hi0 + 3 * (kImg / 16);
-              const uint32_t acc = (kb | ks) != 0;
+              const uint32_t acc = (kb > kb0 || ks > 0) ? 1u : 0u;
               if (ws) {                 // b_hi read once for 4 instructions, b_lo once for 2
                 tc_mma_ws_fill0(d0, a_hi0, b_hi, idesc, acc);
                 tc_mma_ws_use0(d1, a_hi1, b_hi, idesc, acc);
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
             }
           }
           tc_commit(empty + stage);
-          if (kb == a.KBn - 1) tc_commit(tfull);
+          if (kb == kb1 - 1) tc_commit(tfull);
         }
         __syncwarp();
         if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
@@ -330,10 +340,12 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     };
     for (int it = 0; next_unit(it, &m, &j); ++it) {
       unsigned char* gimg = a.aimg + (size_t)m * a.KBn * (2 * kImg);
+      const int kb0 = (j >> 16) * a.kchunk, kb1 = min(a.KBn, kb0 + a.kchunk);
+      j &= 0xffff;
       if constexpr (PREP) {
         const int cw = warp - 2;
         const int c8 = lane & 7, rsub = lane >> 3;
-        const bool first = (j == 0);            // splits x for the whole M tile and checks its range
+        const bool first = (j == 0);            // splits x for the whole M tile (K chunk) and checks its range
         const bool sq = a.quad != 0;            // feeds the x^2 GEMM of this unit through shared memory
         const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
         auto split = [](const float4& v, uint2* hv, uint2* lv) {
@@ -348,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int64_t b = b0 + 4 * i;
-            v[i] = (b < a.B && f0 < a.D) ? ldg_stream(a.x + b * a.D + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = (b < a.B && f0 < a.D) ? ldg_stream(a.x + b * a.lda + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
         auto convert = [&](int kb, float4 (&buf)[8]) {
@@ -358,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 v = buf[i];
+            v.x *= a.ascale; v.y *= a.ascale; v.z *= a.ascale; v.w *= a.ascale;
             const uint32_t row = cw * 32 + 4 * i + rsub;
             const uint32_t off = sw64_off(row, c8 >> 1) + (c8 & 1) * 8;
             uint2 hv, lv;
@@ -380,14 +393,14 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         };
         // two register sets, loads two K blocks ahead of their use (no register copies: a copy would wait for the load)
         float4 bufA[8], bufB[8];
-        load(0, bufA);
-        if (a.KBn > 1) load(1, bufB);
-        for (int kb = 0; kb < a.KBn; kb += 2) {
+        load(kb0, bufA);
+        if (kb0 + 1 < kb1) load(kb0 + 1, bufB);
+        for (int kb = kb0; kb < kb1; kb += 2) {
           convert(kb, bufA);
-          if (kb + 2 < a.KBn) load(kb + 2, bufA);
-          if (kb + 1 < a.KBn) {
+          if (kb + 2 < kb1) load(kb + 2, bufA);
+          if (kb + 1 < kb1) {
             convert(kb + 1, bufB);
-            if (kb + 3 < a.KBn) load(kb + 3, bufB);
+            if (kb + 3 < kb1) load(kb + 3, bufB);
           }
         }
       } else {
@@ -395,8 +408,8 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         // [16 t + 4096 i, +16), i = 0..7, of each 32 KB stage image, handled as two groups of 4 pieces; three
         // groups (1.5 stages, 48 registers) are in flight per thread.  Explicit scalars: a load destination must
         // never be spilled or copied (either would wait for the load and kill the prefetch).
-        const uint4* src = reinterpret_cast<const uint4*>(gimg) + ft;
-        const int NG = 2 * a.KBn;
+        const uint4* src = reinterpret_cast<const uint4*>(gimg) + ft + (size_t)kb0 * (2 * kImg / 16);
+        const int NG = 2 * (kb1 - kb0);
 #define DPK_FETCH(G, n)                                                                           \
   {                                                                                               \
     const uint4* p_ = src + (size_t)((n) >> 1) * (2 * kImg / 16) + ((n) & 1) * 1024;              \
@@ -444,6 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     const float* sqwl = sqw + lane;
     for (int it = 0; next_unit(it, &m, &j); ++it) {
       constexpr bool isS = PREP;
+      j &= 0xffff;
       const int col_base = j * kMmaTileN;
       const int cols = (isS ? a.G0 : a.Ntot) - col_base;
       const bool quad = !isS && a.quad;
@@ -509,6 +523,14 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
             for (int i = 0; i < 32; ++i) {
               if (i < nvalid && bok) *op = -0.5f * __uint_as_float(v[i]);
               op += a.Bp;
+            }
+          } else if (a.linear == 2) {
+            // split-K partial sums: accumulate into the row-major result
+            if (b < a.B) {
+              float* op = a.out + (size_t)b * a.Ntot + col_base + col0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) atomicAdd(op + i, __uint_as_float(v[i]) * a.oscale);
             }
           } else if (a.linear) {
             // generic layer: row-major output, this thread owns 32 consecutive columns of its row
@@ -672,6 +694,73 @@ __global__ void linear_exact_rows_kernel(const float* __restrict__ x, const floa
   }
 }
 
+// ---- leaf moments of the backward / E-step as a GEMM ---------------------------------------------------
+// S1[(g,k), f] = sum_b P[(g,k), b] x[b, f],  S2 = sum_b P x^2,  S0 = sum_b P   (P = dLL/d leaf-LL, [G0*K][Bp]):
+// the contraction runs over the batch, so P (sample-minor already) is the K-major A operand and the transposed
+// inputs XT = [x | x^2 | 1]^T ((2D+1) rows of Bp samples) play the role of the weights.
+// XT rows: f < D: x[:, f];  D <= f < 2D: x^2;  f == 2D: ones (valid samples).  Non-finite inputs raise *flag.
+__global__ void stats_transpose_kernel(const float* __restrict__ x, int64_t B, int64_t Bp, int D, int quad,
+                                       float* __restrict__ xt, int* __restrict__ flag) {
+  __shared__ float tile[32][33];
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const int f0 = blockIdx.y * 32;
+  bool bad = false;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t b = b0 + i;
+    const int f = f0 + threadIdx.x;
+    float v = 0.f;
+    if (b < B && f < D) {
+      v = x[b * D + f];
+      if (!(fabsf(v) <= FLT_MAX)) { bad = true; v = 0.f; }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (bad) *flag = 1;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int f = f0 + i;
+    const int64_t b = b0 + threadIdx.x;
+    if (f < D && b < Bp) {
+      const float v = tile[threadIdx.x][i];
+      xt[(size_t)f * Bp + b] = v;
+      if (quad) xt[(size_t)(D + f) * Bp + b] = v * v;
+    }
+  }
+  if (blockIdx.y == 0)
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < 32; i += 32 * blockDim.y) {
+      const int64_t b = b0 + i;
+      if (b < Bp) xt[(size_t)(quad ? 2 : 1) * D * Bp + b] = (b < B) ? 1.f : 0.f;
+    }
+}
+
+// fb[0] = any of: flagged P rows (out of the fp16 range), inputs non-finite / out of range
+__global__ void stats_flag_kernel(const int* __restrict__ redo, int n_redo, const int* __restrict__ wflag,
+                                  const int* __restrict__ xflag, int* __restrict__ fb) {
+  int any = (*wflag != 0) || (*xflag != 0);
+  for (int i = threadIdx.x; i < n_redo; i += blockDim.x) any |= redo[i];
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) *fb = any;
+}
+
+// dense S[(g,k)][F] -> the (G0, K, dim) accumulators of ratspn_bwd.cu (skipped when the fallback flag is set)
+__global__ void stats_gather_kernel(const float* __restrict__ S, const int32_t* __restrict__ mask,
+                                    const int32_t* __restrict__ region_len, int G0, int K, int dim, int D, int F, int quad,
+                                    const int* __restrict__ fb, float* __restrict__ s1, float* __restrict__ s2,
+                                    float* __restrict__ s0tot) {
+  if (*fb) return;
+  const int64_t total = (int64_t)G0 * K * dim;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % dim);
+    const int n = (int)(idx / dim);
+    const int g = n / K;
+    if (d == 0) s0tot[n] += S[(size_t)n * F + (quad ? 2 : 1) * D];
+    if (d >= region_len[g]) continue;
+    const int f = mask[(size_t)g * dim + d];
+    s1[idx] += S[(size_t)n * F + f];
+    if (quad) s2[idx] += S[(size_t)n * F + D + f];
+  }
+}
+
 }  // namespace
 
 // flags block (ints): redo[Bp/32] | unit counters [2] | pad | wflag | debug stats (32 x 8 bytes).
@@ -723,7 +812,7 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.wflag = a.redo + p.Bp / 32 + 3;
   DPK_CUDA_TRY(cudaMemsetAsync(a.redo, 0, mma_call_flag_ints(p) * 4, st));
   a.xlimit = a.quad ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
-  a.linear = 0; a.relu = 0;
+  a.linear = 0; a.relu = 0; a.nC = 1; a.kchunk = a.KBn; a.ascale = 1.f; a.oscale = 1.f; a.lda = a.D;
   const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
   a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.redo + p.Bp / 32 + 4) : nullptr;
   if (want_stats) DPK_CUDA_TRY(cudaMemsetAsync(a.stats, 0, 32 * 8, st));
@@ -755,6 +844,66 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
               q[8] ? (double)q[6] / q[8] : 0.0);
     }
   }
+  return DPK_OK;
+}
+
+// ---- leaf moments as a GEMM: host side -----------------------------------------------------------------
+// Workspace (RatPlan::off_stats_*): XT fp32 | its operand images | operand images of P | dense S | flags.
+// On return *fallback points at a device flag: != 0 -> the caller's exact CUDA-core kernel must do the work.
+int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, const float* g0, float* ws,
+                              float* s1, float* s2, float* s0tot, const int** fallback, cudaStream_t st) {
+  const int quad = (p.kind == DPK_LEAF_GAUSSIAN) ? 1 : 0;
+  const int F = (quad ? 2 : 1) * p.D + 1, N = p.G0 * p.K;
+  const int KBn = (int)(p.Bp / kMmaKB);
+  const int nM = (int)ceil_div(N, kMmaTileM), nW = (int)ceil_div(F, kMmaTileN);
+  float* xt = ws + p.off_stats_xt;
+  unsigned char* wimg = reinterpret_cast<unsigned char*>(ws + p.off_stats_wimg);
+  unsigned char* aimg = reinterpret_cast<unsigned char*>(ws + p.off_stats_aimg);
+  float* S = ws + p.off_stats_s;
+  int* flg = reinterpret_cast<int*>(ws + p.off_stats_flags);
+  const int n_redo = (int)(round_up(N, 128) / 32);
+  // flags: redo[n_redo] | unit counters [2] | pad | wflag | xflag | fb
+  int* wflag = flg + n_redo + 3; int* xflag = flg + n_redo + 4; int* fb = flg + n_redo + 5;
+  DPK_CUDA_TRY(cudaMemsetAsync(flg, 0, (size_t)(n_redo + 6) * 4, st));
+  DPK_CUDA_TRY(cudaMemsetAsync(S, 0, (size_t)N * F * 4, st));
+  DPK_CUDA_TRY(cudaMemsetAsync(wimg, 0, (size_t)nW * KBn * 2 * kImg, st));
+  {
+    dim3 grid((unsigned)(p.Bp / 32), (unsigned)ceil_div(p.D, 32));
+    stats_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(x, p.B, p.Bp, p.D, quad, xt, xflag);
+    DPK_LAUNCH_CHECK("stats_transpose_kernel");
+    const int64_t total = (int64_t)F * p.Bp;
+    linear_prep_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 16384), 256, 0, st>>>(
+        xt, F, (int)p.Bp, KBn, wimg, wflag);
+    DPK_LAUNCH_CHECK("linear_prep_weight_kernel (stats)");
+  }
+  LeafMmaArgs a;
+  a.x = g0; a.B = N; a.Bp = round_up(N, 128);
+  a.lda = p.Bp; a.D = (p.B % 4 == 0) ? (int)p.B : (int)p.Bp;   // pad samples of P are never read when B % 4 == 0
+  a.quad = 0; a.G0 = 0; a.K = 1; a.Ntot = F;
+  a.nS = 0; a.nW = nW; a.KBn = KBn; a.last_ks = 2;
+  a.nM = nM;
+  a.mma_mode = env_int("DPK_MMA_MODE", 1);
+  a.wimg = wimg; a.simg = nullptr; a.aimg = aimg;
+  a.cstm = nullptr; a.sq = nullptr; a.out = S;
+  a.redo = flg; a.unit_counter = flg + n_redo; a.wflag = wflag;
+  // P = posterior * grad_out: 2^14 keeps posteriors in [0, 1] inside the fp16 range and drops the subnormal floor
+  a.ascale = 16384.f; a.oscale = 1.f / 16384.f; a.xlimit = 60000.f;
+  a.linear = 2; a.relu = 0; a.stats = nullptr;
+  a.kchunk = 64; a.nC = (int)ceil_div(KBn, a.kchunk);   // <= 384 accumulations per accumulator: 2e-5 relative
+  const int cap = sm_count();
+  const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ratspn_leaf_mma_kernel<true><<<std::min(cap, nM * a.nC), kThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<prep> (stats)");
+  ratspn_leaf_mma_kernel<false><<<std::min(cap, nM * nW * a.nC), kThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main> (stats)");
+  stats_flag_kernel<<<1, 256, 0, st>>>(flg, n_redo, wflag, xflag, fb);
+  const int64_t total = (int64_t)N * p.dim;
+  stats_gather_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 4096), 256, 0, st>>>(
+      S, d->mask, d->region_len, p.G0, p.K, p.dim, p.D, F, quad, fb, s1, s2, s0tot);
+  DPK_LAUNCH_CHECK("stats_gather_kernel");
+  *fallback = fb;
   return DPK_OK;
 }
 
@@ -812,6 +961,7 @@ extern "C" int dpk_linear_forward(const float* x, const float* weight, const flo
   a.cstm = bias; a.sq = nullptr; a.out = out;
   a.redo = flg; a.unit_counter = flg + p.Bp / 32; a.wflag = flg + p.Bp / 32 + 3;
   a.xlimit = 60000.f; a.linear = 1; a.relu = relu ? 1 : 0; a.stats = nullptr;
+  a.nC = 1; a.kchunk = a.KBn; a.ascale = 1.f; a.oscale = 1.f; a.lda = a.D;
   if (!(flags & DPK_F_TABLES_VALID)) {
     ProfScope prof(CAT_PREP, st, 1);
     DPK_CUDA_TRY(cudaMemsetAsync(ws + p.off_wimg, 0, (size_t)p.nW * p.KBn * 2 * kImg, st));

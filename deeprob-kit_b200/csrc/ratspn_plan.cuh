@@ -51,6 +51,8 @@ struct RatPlan {
   // backward scratch (only with DPK_F_SAVE_ACTIVATIONS): posterior-count accumulators in the chunked
   // weight layouts and leaf moment accumulators in the parameter layout (G0,K,dim)
   size_t off_wstat[DPK_MAX_LEVELS], off_rstat, off_s1, off_s2, off_snan, off_s0tot;
+  int stats_mma;   // leaf moments of the backward as a tensor-core GEMM (ratspn_leaf_mma.cu)
+  size_t off_stats_xt, off_stats_wimg, off_stats_aimg, off_stats_s, off_stats_flags;
   size_t stat_begin, stat_end;  // [stat_begin, stat_end) is zero-filled at the start of a backward
   size_t total_floats;
 };
@@ -194,6 +196,7 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
   for (int l = 0; l < p->depth; ++l)
     p->off_gact[l] = (flags & DPK_F_SAVE_ACTIVATIONS) ? take((size_t)p->act_regions[l] * p->act_ch[l] * p->Bp) : 0;
   p->stat_begin = p->stat_end = off;
+  p->stats_mma = 0;
   if (flags & DPK_F_SAVE_ACTIVATIONS) {
     for (int e = 0; e < p->n_sum; ++e) p->off_wstat[e] = take(p->w_floats[e]);
     p->off_rstat = take(p->r_floats);
@@ -203,6 +206,22 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     p->off_snan = take(leaf);
     p->off_s0tot = take((size_t)p->G0 * p->K);
     p->stat_end = off;
+    // leaf moments as a GEMM over the batch (large batches; DPK_STATS_MMA=0 disables, =1 forces)
+    {
+      const int knob = env_int("DPK_STATS_MMA", -1);
+      const size_t mma_smem = (size_t)kMmaStages * 4 * kMmaTileN * kMmaKB * 2 + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+      p->stats_mma = (knob != 0 && (batch >= kMmaMinBatch || knob == 1) && mma_smem <= (size_t)max_dynamic_smem()) ? 1 : 0;
+      if (p->stats_mma) {
+        const int quad = (p->kind == DPK_LEAF_GAUSSIAN) ? 1 : 0;
+        const size_t F = (size_t)(quad ? 2 : 1) * p->D + 1, N = (size_t)p->G0 * p->K;
+        const size_t KBn = (size_t)p->Bp / kMmaKB, img_floats = (size_t)kMmaTileN * kMmaKB * 2 / 4;
+        p->off_stats_xt = take(F * p->Bp);
+        p->off_stats_wimg = take((size_t)ceil_div(F, kMmaTileN) * KBn * 2 * img_floats);
+        p->off_stats_aimg = take((size_t)ceil_div(N, kMmaTileM) * KBn * 2 * img_floats);
+        p->off_stats_s = take(N * F);
+        p->off_stats_flags = take((size_t)round_up(N, 128) / 32 + 8);
+      }
+    }
   }
   p->total_floats = off;
   return DPK_OK;

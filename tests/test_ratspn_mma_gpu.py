@@ -219,3 +219,49 @@ def test_mma_einsum_gradients(monkeypatch):
     assert norm_err(model.root_layer.weight.grad, truth["root"].float()) < tol
     for a, b in zip([l.weight.grad for l in model._sum_layers()], truth["sums"]):
         assert norm_err(a, b.float()) < tol
+
+
+# ---- leaf moments of the backward / E-step as a GEMM over the batch (ratspn_run_leaf_stats_mma) ----------------
+@pytest.mark.parametrize("name", ["gauss784", "gauss36", "bern784", "gauss_scale"])
+def test_mma_leaf_statistics_match_float64_oracle(name, monkeypatch):
+    cfg = dict(CASES["gauss784"], optimize_scale=True, batch=520) if name == "gauss_scale" else dict(CASES[name])
+    if cfg["batch"] % 4:
+        cfg["batch"] += 4 - cfg["batch"] % 4
+    orc = oracle_for(cfg)[0].double()
+    x, g = pg.ratspn_inputs(cfg)
+    ref = orc.em_statistics(x.double()) if cfg["out_classes"] == 1 else None
+    res = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("DPK_STATS_MMA", knob)
+        model = product_model(cfg, DEV, scale_grad=(name == "gauss_scale"))
+        if ref is not None:
+            res[knob] = model.em_statistics(x.to(DEV))
+        else:       # classes > 1: exercise the same kernels through the gradient path
+            with torch.enable_grad():
+                out = model(x.to(DEV))
+                (out * g.to(DEV)).sum().backward()
+            p = model.base_layer.loc if cfg["kind"] == "gaussian" else model.base_layer.logits
+            res[knob] = {"grad": p.grad.clone()}
+    if ref is not None:
+        tol = 1e-4 + 4e-7 * float(res["1"]["ll"].abs().max())
+        for key in ("s0", "s1", "s2"):
+            if res["1"].get(key) is None:      # Bernoulli / frozen unit scale: no second moment
+                continue
+            assert norm_err(res["1"][key], ref[key]) < tol, key
+            assert norm_err(res["1"][key], res["0"][key]) < tol, key
+    else:
+        assert norm_err(res["1"]["grad"], res["0"]["grad"]) < 2e-4
+
+
+def test_mma_leaf_statistics_nan_inputs_fall_back(monkeypatch):
+    cfg = dict(CASES["gauss784_nan"])
+    monkeypatch.setenv("DPK_STATS_MMA", "1")
+    model = product_model(cfg, DEV, scale_grad=False)
+    orc = oracle_for(cfg)[0].double()
+    x, _ = pg.ratspn_inputs(cfg)
+    st = model.em_statistics(x.to(DEV))
+    ref = orc.em_statistics(x.double())
+    tol = 1e-4 + 4e-7 * float(st["ll"].abs().max())
+    for key in ("s0", "s1", "s2"):
+        if st.get(key) is not None:
+            assert norm_err(st[key], ref[key]) < tol, key
