@@ -184,6 +184,145 @@ __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_kernel(const Ei
   }
 }
 
+// Register-resident variant for the common sizes (Kin, OC in {2,4,8,10,16}, one output chunk): a thread keeps the
+// right-hand exps and the dL/dr accumulators of its ST samples in registers (j loop fully unrolled), the partition's
+// whole weight block sits in shared memory; only what phase B needs (q, el, er) goes through shared memory.
+template <int OC, int KIN, int ST>
+__global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_reg_kernel(const EinsumBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NS = kBwdThreads * ST;
+  constexpr int QS = (OC + 3) / 4 * 4;
+  constexpr int K2 = KIN * KIN, KS = KIN | 1;
+  float* q_sm = sm;                          // [NS][QS]   (16-byte aligned rows)
+  float* el = q_sm + (size_t)NS * QS;        // [NS][KS]
+  float* er = el + (size_t)NS * KS;
+  float* wsm = er + (size_t)NS * KS;         // [K2][OC]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p = blockIdx.y;
+  const int64_t base = (int64_t)blockIdx.x * NS;
+  const float* __restrict__ lin = a.in + (size_t)(2 * p) * KIN * a.Bp;
+  const float* __restrict__ rin = lin + (size_t)KIN * a.Bp;
+  const float* __restrict__ wp = a.wsoft + (size_t)p * K2 * OC;
+  for (int t = tid; t < K2 * OC / 2; t += kBwdThreads)
+    reinterpret_cast<float2*>(wsm)[t] = __ldg(reinterpret_cast<const float2*>(wp) + t);
+
+  float elr[ST][KIN], err[ST][KIN], gr[ST][KIN], q[ST][OC];
+#pragma unroll
+  for (int s = 0; s < ST; ++s) {
+    const int row = tid + s * kBwdThreads;
+    const int64_t b = base + row;
+    const bool inb = b < a.B;
+    float vl = -INFINITY, vr = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+      elr[s][k] = inb ? lin[(size_t)k * a.Bp + b] : 0.f;
+      err[s][k] = inb ? rin[(size_t)k * a.Bp + b] : 0.f;
+      vl = fmaxf(vl, elr[s][k]); vr = fmaxf(vr, err[s][k]);
+    }
+    const float ml = (fabsf(vl) <= FLT_MAX) ? vl : 0.f;
+    const float mr = (fabsf(vr) <= FLT_MAX) ? vr : 0.f;
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+      elr[s][k] = __expf(elr[s][k] - ml);
+      err[s][k] = __expf(err[s][k] - mr);
+      el[row * KS + k] = elr[s][k];
+      er[row * KS + k] = err[s][k];
+      gr[s][k] = 0.f;
+    }
+#pragma unroll
+    for (int o = 0; o < OC; ++o) {
+      float qv = 0.f;
+      if (o < a.O && inb) {
+        const size_t at = a.root ? (size_t)b * a.O + o : ((size_t)p * a.O + o) * a.Bp + b;
+        const float yv = a.y[at];
+        const float g = a.gy ? a.gy[at] : 1.f;
+        if (fabsf(yv) <= FLT_MAX && g != 0.f) qv = g * __expf(fminf(ml + mr - yv, 80.f));
+      }
+      q[s][o] = qv;
+      q_sm[row * QS + o] = qv;
+    }
+  }
+  __syncthreads();  // weights, q, el, er of every sample of the CTA are staged
+  // ---- phase A: dL/dl_i = el_i sum_j er_j T_ij,  dL/dr_j = er_j sum_i el_i T_ij,  T_ij = sum_o q_o w[ij][o] ----
+  float* __restrict__ gl_out = a.gin ? a.gin + (size_t)(2 * p) * KIN * a.Bp : nullptr;
+#pragma unroll 1
+  for (int i = 0; i < KIN; ++i) {
+    float si[ST];
+#pragma unroll
+    for (int s = 0; s < ST; ++s) si[s] = 0.f;
+    const float* wrow = wsm + i * KIN * OC;
+#pragma unroll
+    for (int j = 0; j < KIN; ++j) {
+      float w[OC];
+      load_row_smem<OC>(wrow + j * OC, w);
+#pragma unroll
+      for (int s = 0; s < ST; ++s) {
+        float T = 0.f;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) T = fmaf(q[s][o], w[o], T);
+        si[s] = fmaf(err[s][j], T, si[s]);
+        // el_i as a runtime-indexed register would spill: take it from shared memory (conflict-free, KS odd)
+        gr[s][j] = fmaf(el[(tid + s * kBwdThreads) * KS + i], T, gr[s][j]);
+      }
+    }
+    if (gl_out) {
+#pragma unroll
+      for (int s = 0; s < ST; ++s) {
+        const int row = tid + s * kBwdThreads;
+        const int64_t b = base + row;
+        if (b < a.Bp) gl_out[(size_t)i * a.Bp + b] = el[row * KS + i] * si[s];
+      }
+    }
+  }
+  if (gl_out) {
+    float* __restrict__ gr_out = gl_out + (size_t)KIN * a.Bp;
+#pragma unroll
+    for (int s = 0; s < ST; ++s) {
+      const int64_t b = base + tid + s * kBwdThreads;
+      if (b >= a.Bp) continue;
+#pragma unroll
+      for (int k = 0; k < KIN; ++k) gr_out[(size_t)k * a.Bp + b] = gr[s][k] * err[s][k];
+    }
+  }
+  // ---- phase B: posterior counts M[ij][o] += q_o el_i er_j (lanes = product index ij, warps split the samples) ----
+  if (a.wstat) {
+    float* __restrict__ ws = a.wstat + (size_t)p * K2 * OC;
+    const int s_begin = warp * (NS / 4), s_end = s_begin + NS / 4;
+    for (int blk = 0; blk < K2; blk += 128) {
+      int ii[4], jj[4];
+      bool ok[4];
+      float m[4][OC];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ij = blk + lane + 32 * t;
+        ok[t] = ij < K2;
+        ii[t] = ok[t] ? ij / KIN : 0;
+        jj[t] = ok[t] ? ij % KIN : 0;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) m[t][o] = 0.f;
+      }
+      for (int srow = s_begin; srow < s_end; ++srow) {
+        float qv[QS];
+        load_row_smem<QS>(q_sm + (size_t)srow * QS, qv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float pe = el[srow * KS + ii[t]] * er[srow * KS + jj[t]];
+#pragma unroll
+          for (int o = 0; o < OC; ++o) m[t][o] = fmaf(qv[o], pe, m[t][o]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (ok[t]) {
+          const int ij = blk + lane + 32 * t;
+#pragma unroll
+          for (int o = 0; o < OC; ++o)
+            if (m[t][o] != 0.f) atomicAdd(ws + (size_t)ij * OC + o, m[t][o]);
+        }
+    }
+  }
+}
+
 // Posterior counts -> gradient w.r.t. the raw logits (or the counts themselves for EM).
 //   mode 0: rows (p, o) of length Kin2, dst (P, O, Kin2);  mode 1: rows c of length P*Kin2, dst (C, P*Kin2)
 __global__ void ratspn_weight_finalize_kernel(const float* __restrict__ wsoft, const float* __restrict__ wstat,
@@ -464,21 +603,64 @@ static int launch_einsum_bwd_t(const EinsumBwdArgs& a, dim3 grid, size_t smem, c
   return DPK_OK;
 }
 
+template <int OC, int KIN>
+static int launch_einsum_bwd_reg_t(const EinsumBwdArgs& a, cudaStream_t st) {
+  constexpr int ST = 2, QS = (OC + 3) / 4 * 4, KS = KIN | 1;
+  auto kern = ratspn_einsum_bwd_reg_kernel<OC, KIN, ST>;
+  const size_t smem = ((size_t)kBwdThreads * ST * (QS + 2 * KS) + (size_t)KIN * KIN * OC) * 4;
+  if (smem > 48 * 1024)
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(a.Bp, kBwdThreads * ST), (unsigned)a.P);
+  ProfScope prof(CAT_BWD_EINSUM, st);
+  kern<<<grid, kBwdThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_einsum_bwd_reg_kernel");
+  return DPK_OK;
+}
+
+template <int OC>
+static int launch_einsum_bwd_reg_k(const EinsumBwdArgs& a, cudaStream_t st) {
+  switch (a.Kin) {
+    case 2: return launch_einsum_bwd_reg_t<OC, 2>(a, st);
+    case 4: return launch_einsum_bwd_reg_t<OC, 4>(a, st);
+    case 8: return launch_einsum_bwd_reg_t<OC, 8>(a, st);
+    case 10: return launch_einsum_bwd_reg_t<OC, 10>(a, st);
+    case 16: return launch_einsum_bwd_reg_t<OC, 16>(a, st);
+  }
+  return 1;  // not covered
+}
+
 static int launch_einsum_bwd(EinsumBwdArgs a, int OC, cudaStream_t st) {
   const size_t smem_max = (size_t)max_dynamic_smem();
+  if (a.nOc == 1 && a.O <= OC && a.B >= 2 * kBwdThreads && env_int("DPK_BWD_GENERIC", 0) == 0) {
+    int rc = 1;   // register-resident fast path for the common sizes
+    switch (OC) {
+      case 2: rc = launch_einsum_bwd_reg_k<2>(a, st); break;
+      case 4: rc = launch_einsum_bwd_reg_k<4>(a, st); break;
+      case 8: rc = launch_einsum_bwd_reg_k<8>(a, st); break;
+      case 10: rc = launch_einsum_bwd_reg_k<10>(a, st); break;
+      case 16: rc = launch_einsum_bwd_reg_k<16>(a, st); break;
+    }
+    if (rc <= 0) return rc;
+  }
   int rows = (int)std::max<size_t>(1, 8192 / ((size_t)a.Kin * OC * 4));
   rows = std::min(rows, a.Kin);
   a.rows_per_chunk = rows;
   const size_t wbytes = (size_t)rows * a.Kin * OC * 4;
   const int KS = a.Kin | 1, QS = (OC + 3) / 4 * 4;
   auto need = [&](int ST) { return (size_t)kBwdThreads * ST * (QS + 4 * KS) * 4 + wbytes; };
-  int ST = 4;
-  if (need(4) > 160 * 1024 || a.B < 4 * kBwdThreads) ST = 1;
+  // samples per thread: 4 amortises the weight broadcasts best but leaves one 4-warp CTA per SM (115 KB of shared
+  // memory at K = O = 10); 2 keeps three CTAs resident -- measured faster on B200 (DPK_BWD_ST overrides)
+  int ST = env_int("DPK_BWD_ST", 2);
+  if (ST != 1 && ST != 2 && ST != 4) ST = 2;
+  if (need(ST) > 160 * 1024 || a.B < (int64_t)ST * kBwdThreads) ST = 1;
   const size_t smem = need(ST);
   if (smem > smem_max) return set_error(DPK_E_ARG, "einsum backward with %d inputs per region does not fit shared memory", a.Kin);
   dim3 grid((unsigned)ceil_div(a.Bp, kBwdThreads * ST), (unsigned)a.P);
-#define DPK_CASE(oc) \
-  case oc: return (ST == 4) ? launch_einsum_bwd_t<oc, 4>(a, grid, smem, st) : launch_einsum_bwd_t<oc, 1>(a, grid, smem, st);
+#define DPK_CASE(oc)                                                                              \
+  case oc:                                                                                        \
+    return (ST == 4) ? launch_einsum_bwd_t<oc, 4>(a, grid, smem, st)                              \
+           : (ST == 2) ? launch_einsum_bwd_t<oc, 2>(a, grid, smem, st)                            \
+                       : launch_einsum_bwd_t<oc, 1>(a, grid, smem, st);
   switch (OC) { DPK_CASE(2) DPK_CASE(4) DPK_CASE(8) DPK_CASE(10) DPK_CASE(16) }
 #undef DPK_CASE
   return set_error(DPK_E_ARG, "unsupported output chunk %d", OC);
