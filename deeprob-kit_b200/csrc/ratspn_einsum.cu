@@ -242,10 +242,10 @@ __global__ void __launch_bounds__(kEinsumThreads) ratspn_einsum_kernel(const Ein
 // the thread's 4 samples live in registers (j loop fully unrolled), the partition's whole weight block
 // sits in shared memory, outputs are accumulated pairwise with packed FFMA2.  Per (i,j) a thread issues
 // 4 FMUL + 4*OC/2 FFMA2 against OC/4 broadcast LDS.128 -> FMA-pipe bound instead of LDS bound.
-template <int OC, int KIN, bool ROOT>
+template <int OC, int KIN, bool ROOT, int ST = 4>
 __global__ void __launch_bounds__(kEinsumThreads) ratspn_einsum_reg_kernel(const EinsumArgs a) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int ST = 4, NS = kEinsumThreads * ST, K2 = KIN * KIN, OH = OC / 2;
+  constexpr int NS = kEinsumThreads * ST, K2 = KIN * KIN, OH = OC / 2;
   float* wsm = sm;              // [K2][OC]
   float* el = wsm + K2 * OC;    // [KIN][NS]
   const int tid = threadIdx.x;
@@ -395,11 +395,17 @@ static int launch_einsum_t(const EinsumArgs& a, dim3 grid, size_t smem, int cat,
 
 template <int OC, int KIN>
 static int launch_einsum_reg_t(const EinsumArgs& a, int cat, cudaStream_t st) {
-  auto kern = ratspn_einsum_reg_kernel<OC, KIN, false>;
-  const size_t smem = ((size_t)KIN * KIN * OC + (size_t)KIN * kEinsumThreads * 4) * 4;
+  // samples per thread: 2 measured fastest on B200 (fewer registers -> more resident CTAs beats the better
+  // amortisation of the weight broadcasts at 4); DPK_EINSUM_ST overrides
+  const int knob = env_int("DPK_EINSUM_ST", 2);
+  const int ST = (knob == 1 || knob == 4) ? knob : 2;
+  auto kern = (ST == 1)   ? ratspn_einsum_reg_kernel<OC, KIN, false, 1>
+              : (ST == 2) ? ratspn_einsum_reg_kernel<OC, KIN, false, 2>
+                          : ratspn_einsum_reg_kernel<OC, KIN, false, 4>;
+  const size_t smem = ((size_t)KIN * KIN * OC + (size_t)KIN * kEinsumThreads * ST) * 4;
   if (smem > 48 * 1024)
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(a.Bp, kEinsumThreads * 4), (unsigned)a.P);
+  dim3 grid((unsigned)ceil_div(a.Bp, kEinsumThreads * ST), (unsigned)a.P);
   ProfScope prof(cat, st);
   kern<<<grid, kEinsumThreads, smem, st>>>(a);
   DPK_LAUNCH_CHECK("ratspn_einsum_reg_kernel");
