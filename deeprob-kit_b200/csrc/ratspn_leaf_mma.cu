@@ -70,6 +70,7 @@ struct LeafMmaArgs {
   int* unit_counter;          // [2] dynamic scheduler of the two launches (zeroed before)
   unsigned char* aimg;        // [nM][KBn][hi | lo][16 KB] fp16 split of x in operand layout, written by the PREP launch
   float xlimit;
+  int gen;                    // general Gaussian: x^2 images go to the global scratch too (K blocks KBn/2 .. KBn-1)
   int64_t lda;                // row stride of x (elements); columns >= D read as 0
   int nC, kchunk;             // split-K: nC chunks of kchunk K blocks (nC == 1: the whole K range per unit)
   float ascale, oscale;       // PREP multiplies the A operand by ascale; linear == 2 multiplies the result by oscale
@@ -347,6 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         const int c8 = lane & 7, rsub = lane >> 3;
         const bool first = (j == 0);            // splits x for the whole M tile (K chunk) and checks its range
         const bool sq = a.quad != 0;            // feeds the x^2 GEMM of this unit through shared memory
+        const bool gen = a.gen != 0;            // x^2 images to the global scratch (second half of the K blocks)
+        const int KBh = gen ? a.KBn / 2 : a.KBn; // K blocks of x itself
         const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
         auto split = [](const float4& v, uint2* hv, uint2* lv) {
           const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
@@ -387,20 +390,27 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
               split(v, &hv, &lv);
               *reinterpret_cast<uint2*>(A + off) = hv;
               *reinterpret_cast<uint2*>(A + kImg + off) = lv;
+            } else if (gen) {
+              v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w;
+              split(v, &hv, &lv);
+              unsigned char* G2 = G + (size_t)KBh * (2 * kImg);
+              *reinterpret_cast<uint2*>(G2 + off) = hv;
+              *reinterpret_cast<uint2*>(G2 + kImg + off) = lv;
             }
           }
           if (sq) publish();
         };
         // two register sets, loads two K blocks ahead of their use (no register copies: a copy would wait for the load)
         float4 bufA[8], bufB[8];
+        const int kbe = min(kb1, KBh);          // the x^2 half of a general Gaussian is written alongside
         load(kb0, bufA);
-        if (kb0 + 1 < kb1) load(kb0 + 1, bufB);
-        for (int kb = kb0; kb < kb1; kb += 2) {
+        if (kb0 + 1 < kbe) load(kb0 + 1, bufB);
+        for (int kb = kb0; kb < kbe; kb += 2) {
           convert(kb, bufA);
-          if (kb + 2 < kb1) load(kb + 2, bufA);
-          if (kb + 1 < kb1) {
+          if (kb + 2 < kbe) load(kb + 2, bufA);
+          if (kb + 1 < kbe) {
             convert(kb + 1, bufB);
-            if (kb + 3 < kb1) load(kb + 3, bufB);
+            if (kb + 3 < kbe) load(kb + 3, bufB);
           }
         }
       } else {
@@ -613,8 +623,11 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
 }
 
 // ---- weight images ---------------------------------------------------------------------------------
+// KIND == DPK_LEAF_GAUSSIAN (general scale p1): two weights per entry, mu/sigma^2 against x (K blocks 0 .. KBn/2-1)
+// and -1/(2 sigma^2) against x^2 (K blocks KBn/2 .. KBn-1); KBn counts both halves.
 template <int KIND>
-__global__ void ratspn_prep_leaf_mma_kernel(const float* __restrict__ p0, const int32_t* __restrict__ mask,
+__global__ void ratspn_prep_leaf_mma_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                            const int32_t* __restrict__ mask,
                                             const int32_t* __restrict__ region_len, int G0, int K, int dim, int KBn,
                                             unsigned char* __restrict__ wimg, unsigned char* __restrict__ simg,
                                             int* __restrict__ wflag) {
@@ -625,7 +638,13 @@ __global__ void ratspn_prep_leaf_mma_kernel(const float* __restrict__ p0, const 
     const int g = (int)(idx / ((int64_t)dim * K));
     if (d >= region_len[g]) continue;          // pad slots contribute exactly 0 (ratspn.py:104-105)
     const int f = mask[(size_t)g * dim + d];
-    const float w = p0[idx];
+    float w = p0[idx], wq = 0.f;
+    if (KIND == DPK_LEAF_GAUSSIAN) {
+      const float inv = 1.0f / p1[idx];
+      wq = -0.5f * inv * inv;
+      w = w * inv * inv;
+      if (!(fabsf(wq) <= 60000.f)) *wflag = 1;
+    }
     if (!(fabsf(w) <= 60000.f)) *wflag = 1;
     const int n = g * K + k;
     const uint32_t off = sw64_off((uint32_t)(n & (kMmaTileN - 1)), (uint32_t)(f & 31) >> 3) + (uint32_t)(f & 7) * 2u;
@@ -634,6 +653,13 @@ __global__ void ratspn_prep_leaf_mma_kernel(const float* __restrict__ p0, const 
     const __half lo = __float2half_rn(w - __half2float(hi));
     *reinterpret_cast<__half*>(img + off) = hi;
     *reinterpret_cast<__half*>(img + kImg + off) = lo;
+    if (KIND == DPK_LEAF_GAUSSIAN) {
+      unsigned char* img2 = img + (size_t)(KBn / 2) * (2 * kImg);
+      const __half qhi = __float2half_rn(wq);
+      const __half qlo = __float2half_rn(wq - __half2float(qhi));
+      *reinterpret_cast<__half*>(img2 + off) = qhi;
+      *reinterpret_cast<__half*>(img2 + kImg + off) = qlo;
+    }
     if (KIND == kLeafGaussUnit && k == 0) {
       const uint32_t soff = sw64_off((uint32_t)(g & (kMmaTileN - 1)), (uint32_t)(f & 31) >> 3) + (uint32_t)(f & 7) * 2u;
       *reinterpret_cast<__half*>(simg + ((size_t)(g / kMmaTileN) * KBn + (f >> 5)) * kImg + soff) = __float2half_rn(1.f);
@@ -642,7 +668,8 @@ __global__ void ratspn_prep_leaf_mma_kernel(const float* __restrict__ p0, const 
 }
 
 template <int KIND>
-__global__ void ratspn_prep_leaf_mma_const_kernel(const float* __restrict__ p0, const int32_t* __restrict__ region_len,
+__global__ void ratspn_prep_leaf_mma_const_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                  const int32_t* __restrict__ region_len,
                                                   int G0, int K, int dim, float* __restrict__ cstm) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= G0 * K) return;
@@ -653,7 +680,10 @@ __global__ void ratspn_prep_leaf_mma_const_kernel(const float* __restrict__ p0, 
   for (int d = 0; d < len; ++d) {
     const float w = p[d];
     if (KIND == kLeafGaussUnit) s += fmaf(-0.5f * w, w, -kLogSqrt2Pi);
-    else s -= fmaxf(w, 0.f) + log1pf(expf(-fabsf(w)));
+    else if (KIND == DPK_LEAF_GAUSSIAN) {
+      const float sg = p1[(size_t)idx * dim + d], t = w / sg;
+      s += fmaf(-0.5f * t, t, -logf(sg) - kLogSqrt2Pi);
+    } else s -= fmaxf(w, 0.f) + log1pf(expf(-fabsf(w)));
   }
   cstm[idx] = s;
 }
@@ -777,16 +807,22 @@ int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* 
   const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
   int* wflag = flags + p.Bp / 32 + 3;
   DPK_CUDA_TRY(cudaMemsetAsync(wflag, 0, 4, st));
+  const int cblocks = (p.G0 * p.K + 127) / 128;
   if (p.fwd_kind == kLeafGaussUnit) {
-    ratspn_prep_leaf_mma_kernel<kLeafGaussUnit><<<blocks, 256, 0, st>>>(d->leaf_p0, d->mask, d->region_len, p.G0, p.K,
-                                                                         p.dim, p.mma_kb, wimg, simg, wflag);
-    ratspn_prep_leaf_mma_const_kernel<kLeafGaussUnit><<<(p.G0 * p.K + 127) / 128, 128, 0, st>>>(
-        d->leaf_p0, d->region_len, p.G0, p.K, p.dim, ws + p.off_cstm);
+    ratspn_prep_leaf_mma_kernel<kLeafGaussUnit><<<blocks, 256, 0, st>>>(d->leaf_p0, nullptr, d->mask, d->region_len, p.G0,
+                                                                         p.K, p.dim, p.mma_kb, wimg, simg, wflag);
+    ratspn_prep_leaf_mma_const_kernel<kLeafGaussUnit><<<cblocks, 128, 0, st>>>(d->leaf_p0, nullptr, d->region_len, p.G0,
+                                                                                p.K, p.dim, ws + p.off_cstm);
+  } else if (p.fwd_kind == DPK_LEAF_GAUSSIAN) {
+    ratspn_prep_leaf_mma_kernel<DPK_LEAF_GAUSSIAN><<<blocks, 256, 0, st>>>(d->leaf_p0, d->leaf_p1, d->mask, d->region_len,
+                                                                            p.G0, p.K, p.dim, p.mma_kb, wimg, simg, wflag);
+    ratspn_prep_leaf_mma_const_kernel<DPK_LEAF_GAUSSIAN><<<cblocks, 128, 0, st>>>(d->leaf_p0, d->leaf_p1, d->region_len,
+                                                                                   p.G0, p.K, p.dim, ws + p.off_cstm);
   } else {
-    ratspn_prep_leaf_mma_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(d->leaf_p0, d->mask, d->region_len, p.G0,
-                                                                             p.K, p.dim, p.mma_kb, wimg, simg, wflag);
-    ratspn_prep_leaf_mma_const_kernel<DPK_LEAF_BERNOULLI><<<(p.G0 * p.K + 127) / 128, 128, 0, st>>>(
-        d->leaf_p0, d->region_len, p.G0, p.K, p.dim, ws + p.off_cstm);
+    ratspn_prep_leaf_mma_kernel<DPK_LEAF_BERNOULLI><<<blocks, 256, 0, st>>>(d->leaf_p0, nullptr, d->mask, d->region_len,
+                                                                             p.G0, p.K, p.dim, p.mma_kb, wimg, simg, wflag);
+    ratspn_prep_leaf_mma_const_kernel<DPK_LEAF_BERNOULLI><<<cblocks, 128, 0, st>>>(d->leaf_p0, nullptr, d->region_len,
+                                                                                    p.G0, p.K, p.dim, ws + p.off_cstm);
   }
   DPK_LAUNCH_CHECK("ratspn_prep_leaf_mma_kernel");
   return DPK_OK;
@@ -796,9 +832,11 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   LeafMmaArgs a;
   a.x = x; a.B = p.B; a.Bp = p.Bp; a.D = p.D;
   a.quad = (p.fwd_kind == kLeafGaussUnit) ? 1 : 0;
+  a.gen = (p.fwd_kind == DPK_LEAF_GAUSSIAN) ? 1 : 0;
   a.G0 = p.G0; a.K = p.K; a.Ntot = p.G0 * p.K;
   a.nS = p.mma_nS; a.nW = p.mma_nW; a.KBn = p.mma_kb;
-  a.last_ks = ((p.D + 15) / 16) % 2 == 1 ? 1 : 2;
+  // (a general Gaussian walks two halves of K blocks: the short last block of each half is zero padded instead)
+  a.last_ks = (a.gen || ((p.D + 15) / 16) % 2 == 0) ? 2 : 1;
   a.nM = (int)ceil_div(p.B, kMmaTileM);
   a.mma_mode = env_int("DPK_MMA_MODE", 1);
   a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_wimg);
@@ -811,7 +849,7 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.unit_counter = a.redo + p.Bp / 32;
   a.wflag = a.redo + p.Bp / 32 + 3;
   DPK_CUDA_TRY(cudaMemsetAsync(a.redo, 0, mma_call_flag_ints(p) * 4, st));
-  a.xlimit = a.quad ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
+  a.xlimit = (a.quad || a.gen) ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
   a.linear = 0; a.relu = 0; a.nC = 1; a.kchunk = a.KBn; a.ascale = 1.f; a.oscale = 1.f; a.lda = a.D;
   const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
   a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.redo + p.Bp / 32 + 4) : nullptr;
@@ -879,7 +917,7 @@ int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const 
   LeafMmaArgs a;
   a.x = g0; a.B = N; a.Bp = round_up(N, 128);
   a.lda = p.Bp; a.D = (p.B % 4 == 0) ? (int)p.B : (int)p.Bp;   // pad samples of P are never read when B % 4 == 0
-  a.quad = 0; a.G0 = 0; a.K = 1; a.Ntot = F;
+  a.quad = 0; a.gen = 0; a.G0 = 0; a.K = 1; a.Ntot = F;
   a.nS = 0; a.nW = nW; a.KBn = KBn; a.last_ks = 2;
   a.nM = nM;
   a.mma_mode = env_int("DPK_MMA_MODE", 1);
@@ -952,7 +990,7 @@ extern "C" int dpk_linear_forward(const float* x, const float* weight, const flo
   int* flg = reinterpret_cast<int*>(ws + p.off_flags);
   LeafMmaArgs a;
   a.x = x; a.B = p.B; a.Bp = p.Bp; a.D = in_features;
-  a.quad = 0; a.G0 = 0; a.K = 1; a.Ntot = out_features;
+  a.quad = 0; a.gen = 0; a.G0 = 0; a.K = 1; a.Ntot = out_features;
   a.nS = 0; a.nW = p.nW; a.KBn = p.KBn;
   a.last_ks = ((in_features + 15) / 16) % 2 == 1 ? 1 : 2;
   a.nM = (int)ceil_div(p.B, kMmaTileM);

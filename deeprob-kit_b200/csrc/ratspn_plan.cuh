@@ -149,12 +149,11 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
   p->off_tab = take((size_t)p->G0 * p->kc.count * p->leaf_nch * p->leaf_chunk_floats);
   p->off_cd = take((size_t)p->G0 * p->kc.count * p->dim * p->kc.chunk);
   p->off_cst = take((size_t)p->G0 * p->kc.padded);
-  // Tensor-core leaf: linear-in-parameters flavours only (unit-scale Gaussian, Bernoulli), 16-byte
-  // loadable rows.  DPK_LEAF_MMA=0 disables it, =1 forces it for any batch size (tests).
+  // Tensor-core leaf (all three flavours), 16-byte loadable rows.  DPK_LEAF_MMA=0 disables it, =1 forces it for any batch size (tests).
   {
     const int knob = env_int("DPK_LEAF_MMA", -1);
     const size_t mma_smem = (size_t)kMmaStages * 4 * kMmaTileN * kMmaKB * 2 + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
-    p->leaf_mma = (p->fwd_kind != DPK_LEAF_GAUSSIAN && p->D % 4 == 0 && knob != 0 &&
+    p->leaf_mma = (p->D % 4 == 0 && knob != 0 &&
                    (batch >= kMmaMinBatch || knob == 1) && mma_smem <= (size_t)max_dynamic_smem())
                       ? 1 : 0;
     p->mma_nS = p->mma_nW = p->mma_kb = 0;
@@ -162,7 +161,8 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     if (p->leaf_mma) {
       p->mma_nS = (p->fwd_kind == kLeafGaussUnit) ? (int)ceil_div(p->G0, kMmaTileN) : 0;
       p->mma_nW = (int)ceil_div((int64_t)p->G0 * p->K, kMmaTileN);
-      p->mma_kb = (int)ceil_div(p->D, kMmaKB);
+      // K blocks of 32 features; a general Gaussian has a second half of them for x^2
+      p->mma_kb = (int)ceil_div(p->D, kMmaKB) * (p->fwd_kind == DPK_LEAF_GAUSSIAN ? 2 : 1);
       const size_t img_floats = (size_t)kMmaTileN * kMmaKB * 2 / 4;
       p->off_wimg = take((size_t)p->mma_nW * p->mma_kb * 2 * img_floats);
       p->off_simg = take((size_t)p->mma_nS * p->mma_kb * img_floats);   // directly behind wimg (one memset)
