@@ -41,7 +41,22 @@ struct CouplingArgs {
   float* ldj;                          // (B) log-det accumulator (+=), may be NULL
   int64_t B;
   int N, w_count, w_inner, affine, direction;  // direction 0: u = (x - t) * exp(-s), ldj -= sum s ; 1: x = u * exp(s) + t, ldj += sum s
+  const int* zmap; int z_half;         // compact conditioner output (forward only): column of element e, offset of the s half
+  const float* post_scale; const float* post_shift; float post_ldj;  // fused per-feature affine after the coupling (eval batch-norm)
+  int vec4;
 };
+
+// One element of the coupling: masked-out elements (m == 0) pass through without touching z, so a conditioner that
+// only produced the live columns (compact z: t = z[zmap[e]], raw s = z[z_half + zmap[e]]) can be consumed directly.
+__device__ __forceinline__ float coupling_elem(const CouplingArgs& a, const float* zr, int e, float m, float xv, float& acc) {
+  if (m == 0.f) return xv;
+  const int zi = a.zmap ? __ldg(a.zmap + e) : e;
+  const float t = m * zr[zi];
+  float s = 0.f;
+  if (a.affine) s = m * __ldg(a.w + (e / a.w_inner) % a.w_count) * tanhf(zr[a.z_half + zi]);
+  acc += s;
+  return a.direction == 0 ? (xv - t) * expf(-s) : xv * expf(s) + t;
+}
 
 __global__ void __launch_bounds__(256) coupling_fwd_kernel(const CouplingArgs a) {
   __shared__ float red[8];
@@ -50,18 +65,37 @@ __global__ void __launch_bounds__(256) coupling_fwd_kernel(const CouplingArgs a)
     const float* zr = a.z + b * a.z_stride;
     float* orow = a.out + b * a.out_stride;
     float acc = 0.f;
-    for (int e = threadIdx.x; e < a.N; e += 256) {
-      const float m = a.inv_mask ? __ldg(a.inv_mask + e) : 1.f;
-      const float t = m * zr[e];
-      float s = 0.f;
-      if (a.affine) s = m * __ldg(a.w + (e / a.w_inner) % a.w_count) * tanhf(zr[a.N + e]);
-      const float xv = xr[e];
-      orow[e] = a.direction == 0 ? (xv - t) * expf(-s) : xv * expf(s) + t;
-      acc += s;
+    if (a.vec4) {
+      // 16-byte loads/stores of x, mask, out (and of the fused batch-norm affine); z through scalar loads
+      for (int e = threadIdx.x * 4; e < a.N; e += 1024) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + e);
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (a.inv_mask) m = __ldg(reinterpret_cast<const float4*>(a.inv_mask + e));
+        float4 r;
+        r.x = coupling_elem(a, zr, e, m.x, xv.x, acc);
+        r.y = coupling_elem(a, zr, e + 1, m.y, xv.y, acc);
+        r.z = coupling_elem(a, zr, e + 2, m.z, xv.z, acc);
+        r.w = coupling_elem(a, zr, e + 3, m.w, xv.w, acc);
+        if (a.post_scale) {
+          const float4 pa = __ldg(reinterpret_cast<const float4*>(a.post_scale + e));
+          const float4 pc = __ldg(reinterpret_cast<const float4*>(a.post_shift + e));
+          r.x = fmaf(r.x, pa.x, pc.x); r.y = fmaf(r.y, pa.y, pc.y);
+          r.z = fmaf(r.z, pa.z, pc.z); r.w = fmaf(r.w, pa.w, pc.w);
+        }
+        *reinterpret_cast<float4*>(orow + e) = r;
+      }
+    } else {
+      for (int e = threadIdx.x; e < a.N; e += 256) {
+        const float m = a.inv_mask ? __ldg(a.inv_mask + e) : 1.f;
+        float r = coupling_elem(a, zr, e, m, xr[e], acc);
+        if (a.post_scale) r = fmaf(r, __ldg(a.post_scale + e), __ldg(a.post_shift + e));
+        orow[e] = r;
+      }
     }
-    if (a.ldj && a.affine) {
-      const float tot = block_sum_256(acc, red);
-      if (threadIdx.x == 0) a.ldj[b] += (a.direction == 0) ? -tot : tot;
+    if (a.ldj) {
+      float tot = 0.f;
+      if (a.affine) tot = block_sum_256(acc, red);
+      if (threadIdx.x == 0 && (a.affine || a.post_ldj != 0.f)) a.ldj[b] += ((a.direction == 0) ? -tot : tot) + a.post_ldj;
     }
   }
 }
@@ -268,6 +302,7 @@ static int fill_coupling(CouplingArgs* a, const dpk_coupling_desc* d, const floa
   a->x = x; a->x_stride = d->x_stride; a->z = z; a->z_stride = d->z_stride; a->inv_mask = d->inv_mask;
   a->w = d->scale_weight; a->out = nullptr; a->out_stride = 0; a->ldj = nullptr; a->B = d->batch; a->N = d->features;
   a->w_count = d->w_count; a->w_inner = d->w_inner; a->affine = d->affine; a->direction = d->direction;
+  a->zmap = nullptr; a->z_half = d->features; a->post_scale = a->post_shift = nullptr; a->post_ldj = 0.f; a->vec4 = 0;
   return DPK_OK;
 }
 
@@ -275,19 +310,43 @@ static int fill_coupling(CouplingArgs* a, const dpk_coupling_desc* d, const floa
 
 using namespace dpk;
 
+static int launch_coupling_fwd(CouplingArgs& a, float* out, int64_t out_stride, float* log_det, void* stream) {
+  if (!out) return set_error(DPK_E_ARG, "coupling: null output");
+  a.out = out; a.out_stride = out_stride; a.ldj = log_det;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  a.vec4 = a.N % 4 == 0 && a.x_stride % 4 == 0 && out_stride % 4 == 0 && al16(a.x) && al16(out) && al16(a.inv_mask) &&
+           al16(a.post_scale) && al16(a.post_shift);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CAT_FLOW, st);
+  coupling_fwd_kernel<<<sample_grid(a.B), 256, 0, st>>>(a);
+  DPK_LAUNCH_CHECK("coupling_fwd_kernel");
+  return DPK_OK;
+}
+
 extern "C" int dpk_coupling_forward(const dpk_coupling_desc* desc, const float* x, const float* z, float* out,
                                     int64_t out_stride, float* log_det, void* stream) {
   CouplingArgs a;
   int rc = fill_coupling(&a, desc, x, z);
   if (rc) return rc;
   if (a.B == 0) return DPK_OK;
-  if (!out) return set_error(DPK_E_ARG, "coupling: null output");
-  a.out = out; a.out_stride = out_stride; a.ldj = log_det;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ProfScope prof(CAT_FLOW, st);
-  coupling_fwd_kernel<<<sample_grid(a.B), 256, 0, st>>>(a);
-  DPK_LAUNCH_CHECK("coupling_fwd_kernel");
-  return DPK_OK;
+  return launch_coupling_fwd(a, out, out_stride, log_det, stream);
+}
+
+extern "C" int dpk_coupling_forward_compact(const dpk_coupling_desc* desc, const float* x, const float* z,
+                                            const int32_t* z_index, int32_t z_half, const float* post_scale,
+                                            const float* post_shift, float post_log_det, float* out,
+                                            int64_t out_stride, float* log_det, void* stream) {
+  CouplingArgs a;
+  int rc = fill_coupling(&a, desc, x, z);
+  if (rc) return rc;
+  if ((post_scale == nullptr) != (post_shift == nullptr)) return set_error(DPK_E_ARG, "coupling: post affine needs scale and shift");
+  if (z_index && (!desc->inv_mask || z_half <= 0)) return set_error(DPK_E_ARG, "coupling: compact z needs inv_mask and z_half");
+  if (post_log_det != 0.f && !log_det) return set_error(DPK_E_ARG, "coupling: post log-det without accumulator");
+  if (a.B == 0) return DPK_OK;
+  a.zmap = z_index;
+  if (z_index) a.z_half = z_half;
+  a.post_scale = post_scale; a.post_shift = post_shift; a.post_ldj = post_log_det;
+  return launch_coupling_fwd(a, out, out_stride, log_det, stream);
 }
 
 extern "C" int dpk_coupling_backward(const dpk_coupling_desc* desc, const float* x, const float* z,

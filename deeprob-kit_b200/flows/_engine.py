@@ -272,28 +272,136 @@ def linear(x, weight, bias, relu, cache=None):
     return out
 
 
-def mlp(network, x):
-    """Evaluate an nn.Sequential of Linear / ReLU layers (the conditioner of CouplingLayer1d,
-    deeprob/flows/layers/coupling.py:45-56).  Inference on a large CUDA batch goes through `linear`; training (any
-    gradient needed), small batches and unusual layer stacks use the stock modules (cuBLAS)."""
+def _mlp_plan(network, x):
+    """[(Linear, relu_follows)] when `network` is a Linear/ReLU stack the tcgen05 GEMM can evaluate for this call
+    (inference on a large fp32 CUDA batch), else None."""
     import os
     from torch import nn
+    if (torch.is_grad_enabled() or not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32
+            or x.shape[0] < MLP_MIN_BATCH or os.environ.get("DPK_LINEAR_MMA", "1") == "0"):
+        return None
     mods = list(network)
-    ok = (not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
-          and x.shape[0] >= MLP_MIN_BATCH and os.environ.get("DPK_LINEAR_MMA", "1") != "0")
     plan = []
     i = 0
-    while ok and i < len(mods):
+    while i < len(mods):
         m = mods[i]
         if type(m) is not nn.Linear or m.in_features % 4 or m.weight.dtype != torch.float32 or not m.weight.is_contiguous():
-            ok = False
-            break
+            return None
         relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
         plan.append((m, relu))
         i += 2 if relu else 1
-    if not ok:
-        return network(x)
-    for m, relu in plan:
+    return plan or None
+
+
+def _derived(cache, name, sources, make):
+    """Tensor derived from parameters, rebuilt IN PLACE (so that its own version counter moves and `linear` refreshes
+    its operand images) only when a source tensor changed."""
+    sig = tuple((t.data_ptr(), t._version) for t in sources)
+    if cache.get(name + "_sig") != sig:
+        new = make()
+        old = cache.get(name)
+        if old is not None and old.shape == new.shape and old.device == new.device:
+            old.copy_(new)
+        else:
+            cache[name] = new.contiguous()
+        cache[name + "_sig"] = sig
+    return cache[name]
+
+
+def mlp(network, x, in_mask=None):
+    """Evaluate an nn.Sequential of Linear / ReLU layers on `in_mask * x` (the conditioner of CouplingLayer1d,
+    deeprob/flows/layers/coupling.py:45-56,72-75).  Inference on a large CUDA batch goes through `linear`, with the
+    0/1 input mask folded into the first layer's weight columns ((m*x) W^T = x (W*m)^T: no masked copy of x is made);
+    training (any gradient needed), small batches and unusual layer stacks use the stock modules (cuBLAS)."""
+    plan = _mlp_plan(network, x)
+    if plan is None:
+        return network(x if in_mask is None else in_mask * x)
+    for li, (m, relu) in enumerate(plan):
         cache = m.__dict__.setdefault("_dpk_linear_cache", {})
-        x = linear(x, m.weight, m.bias, relu, cache)
+        weight = m.weight
+        if li == 0 and in_mask is not None:
+            weight = _derived(cache, "masked_w", (m.weight, in_mask), lambda: m.weight.detach() * in_mask.reshape(1, -1))
+        x = linear(x, weight, m.bias, relu, cache)
     return x
+
+
+def eval_batch_norm_affine(bn):
+    """(a, c, log_det) of an eval-mode batch-norm bijector in the density direction, u = a*x + c
+    (deeprob/flows/utils.py:118-139 with the running statistics); cached on the layer until a tensor changes
+    (one host read of the log-det constant per change)."""
+    ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    sig = tuple((t.data_ptr(), t._version) for t in ts)
+    c = bn.__dict__.get("_dpk_eval_cache")
+    if c is None or c[0] != sig:
+        with torch.no_grad():
+            veps = bn.running_var.reshape(-1).float() + bn.eps
+            w = bn.weight.reshape(-1).float()
+            a = (torch.rsqrt(veps) * torch.exp(w)).contiguous()
+            shift = (bn.bias.reshape(-1).float() - bn.running_mean.reshape(-1).float() * a).contiguous()
+            ldj = float(torch.sum(w - 0.5 * torch.log(veps)))
+        c = (sig, a, shift, ldj)
+        bn.__dict__["_dpk_eval_cache"] = c
+    return c[1], c[2], c[3]
+
+
+def coupling1d_infer(layer, x, direction, bn=None):
+    """Inference fast path of CouplingLayer1d (deeprob/flows/layers/coupling.py:72-104): returns (out, log_det) or
+    None when it does not apply (gradients needed, small batch, unusual conditioner).
+
+    The reference evaluates the conditioner on mask*x and multiplies t and s by inv_mask, so (a) the input columns
+    with mask == 0 and (b) the output columns with inv_mask == 0 never reach the result.  Here the first Linear runs
+    on the gathered live input columns (K halves), the last Linear only produces the live t|s columns (N halves),
+    and the coupling kernel reads that compact z; `bn` (an eval-mode BatchNormLayer1d that follows in the density
+    direction) is applied in the same pass."""
+    import os
+    plan = _mlp_plan(layer.network, x)
+    if plan is None or len(plan) < 2 or os.environ.get("DPK_FLOW_COMPACT", "1") == "0":
+        return None
+    x = x.contiguous()
+    batch, n = x.shape
+    cache = layer.__dict__.setdefault("_dpk_cache", {})
+    key = (str(x.device), layer.mask._version, layer.inv_mask._version)
+    if cache.get("key") != key:
+        mask, inv = layer.mask.reshape(-1), layer.inv_mask.reshape(-1)
+        live_in = torch.nonzero(mask != 0).reshape(-1)
+        live_out = torch.nonzero(inv != 0).reshape(-1)
+        zmap = torch.zeros(n, dtype=torch.int32, device=x.device)
+        zmap[live_out] = torch.arange(live_out.numel(), dtype=torch.int32, device=x.device)
+        rows = torch.cat([live_out, live_out + n]) if layer.affine else live_out
+        binary = bool(((mask == 0) | (mask == 1)).all())
+        cache.clear()
+        cache.update(key=key, live_in=live_in, live_out=live_out, zmap=zmap, rows=rows, binary=binary)
+    live_in, live_out, rows = cache["live_in"], cache["live_out"], cache["rows"]
+    if live_out.numel() == 0:
+        return None
+    first, last = plan[0][0], plan[-1][0]
+    # first layer: gathered live columns when the mask is 0/1 and their count keeps 16-byte rows, else the fold
+    if cache["binary"] and live_in.numel() and live_in.numel() % 4 == 0:
+        h = x.index_select(1, live_in)
+        w0 = _derived(cache, "w_first", (first.weight,), lambda: first.weight.detach().index_select(1, live_in))
+    else:
+        h = x
+        w0 = _derived(cache, "w_first", (first.weight, layer.mask),
+                      lambda: first.weight.detach() * layer.mask.reshape(1, -1))
+    h = linear(h, w0, first.bias, plan[0][1], first.__dict__.setdefault("_dpk_linear_cache", {}))
+    for m, relu in plan[1:-1]:
+        h = linear(h, m.weight, m.bias, relu, m.__dict__.setdefault("_dpk_linear_cache", {}))
+    w_l = _derived(cache, "w_last", (last.weight,), lambda: last.weight.detach().index_select(0, rows))
+    b_l = None
+    if last.bias is not None:
+        b_l = _derived(cache, "b_last", (last.bias,), lambda: last.bias.detach().index_select(0, rows))
+    z = linear(h, w_l, b_l, plan[-1][1], last.__dict__.setdefault("_dpk_linear_cache", {}))
+    w = _f32c(layer.scale_act.weight.detach()).reshape(-1) if layer.affine else None
+    post_a = post_c = None
+    post_ldj = 0.0
+    if bn is not None:
+        post_a, post_c, post_ldj = eval_batch_norm_affine(bn)
+    out = torch.empty_like(x)
+    ldj = torch.zeros(batch, dtype=torch.float32, device=x.device)
+    d = _coupling_desc(batch, n, layer.affine, direction, w, 1, n, z.shape[1], layer.inv_mask)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dpk_coupling_forward_compact(
+            ctypes.byref(d), _ptr(x), _ptr(z), _ptr(cache["zmap"]), live_out.numel(), _ptr(post_a), _ptr(post_c),
+            ctypes.c_float(post_ldj), _ptr(out), n, _ptr(ldj), _stream(x.device))
+    _lib.check(rc, "dpk_coupling_forward_compact")
+    return out, ldj

@@ -39,14 +39,25 @@ class CouplingLayer1d(Bijector):
         mask = np.arange(self.in_features) % 2
         return mask, 1.0 - mask
 
-    def _transform(self, x, direction):
-        z = _engine.mlp(self.network, self.mask * x)
+    def _transform(self, x, direction, bn=None):
+        # inference: compact conditioner (live input / output columns only) + optional fused eval batch-norm
+        fast = _engine.coupling1d_infer(self, x, direction, bn)
+        if fast is not None:
+            return fast
+        if bn is not None:
+            return None
+        z = _engine.mlp(self.network, x, self.mask)
         w = self.scale_act.weight if self.affine else None
         out, ldj = _engine.coupling(x, z, w, self.inv_mask, self.in_features, 0, self.affine, direction, 1)
         return out, (ldj if self.affine else 0.0)
 
     def apply_backward(self, x):
         return self._transform(x, 0)
+
+    def apply_backward_with(self, x, bn):
+        """apply_backward of this layer followed by apply_backward of the eval-mode batch-norm bijector `bn`, in one
+        pass when the inference fast path applies; None otherwise (the caller then runs the two layers)."""
+        return self._transform(x, 0, bn)
 
     def apply_forward(self, u):
         return self._transform(u, 1)

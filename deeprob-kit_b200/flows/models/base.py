@@ -6,7 +6,8 @@ from torch import distributions, nn
 
 from ...torch.base import DensityEstimator, ProbabilisticModel
 from .. import _engine
-from ..utils import DequantizeLayer, LogitLayer
+from ..layers.coupling import CouplingLayer1d
+from ..utils import BatchNormLayer1d, DequantizeLayer, LogitLayer
 
 
 class NormalizingFlow(ProbabilisticModel):
@@ -115,9 +116,22 @@ class NormalizingFlow(ProbabilisticModel):
 
     def apply_backward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         total = 0.0
-        for layer in self.layers:
+        layers = list(self.layers)
+        i = 0
+        while i < len(layers):
+            layer = layers[i]
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            # coupling + eval-mode batch-norm as one pass (inference fast path, flows/_engine.py coupling1d_infer)
+            if isinstance(layer, CouplingLayer1d) and isinstance(nxt, BatchNormLayer1d) and not nxt.training:
+                fused = layer.apply_backward_with(x, nxt)
+                if fused is not None:
+                    x, ildj = fused
+                    total = total + ildj
+                    i += 2
+                    continue
             x, ildj = layer.apply_backward(x)
             total = total + ildj
+            i += 1
         return x, total
 
     def apply_forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -3,7 +3,7 @@
   config 3b DgcSpn((1,28,28), n_batch=16, sum_channels=32, depthwise=True, n_pooling=2)  (MNIST example setting)
   config 4  RealNVP1d(3072, n_flows=8, depth=2, units=512), batch 16384
   config 1  BernoulliRatSpn(15, 3, 4, 4, 2) on all 2^15 states
-Prints one JSON line per config:   python profiles/bench_configs.py [--no-cpu]"""
+Prints one JSON line per config:   python profiles/bench_configs.py [--no-cpu] [--only NAME]"""
 import json
 import os
 import sys
@@ -20,6 +20,12 @@ from deeprob_kit_b200.flows.models import RealNVP1d  # noqa: E402
 from deeprob_kit_b200.spn.models import BernoulliRatSpn, DgcSpn  # noqa: E402
 
 NO_CPU = "--no-cpu" in sys.argv
+ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""      # substring of a config name
+
+
+def want(name):
+    return ONLY in name
+
 
 
 def gpu_time(model, x, steps=10, grad=False):
@@ -77,6 +83,8 @@ def dgc_oracle_fn(model):
 torch.manual_seed(0)
 for name, kw, batch in (("dgcspn_28x28_c8", dict(n_batch=8, sum_channels=8, depthwise=True), 32768),
                         ("dgcspn_28x28_mnist_example", dict(n_batch=16, sum_channels=32, depthwise=True, n_pooling=2), 32768)):
+    if not want(name):
+        continue
     m = DgcSpn((1, 28, 28), **kw).cuda().eval()
     x = torch.randn(batch, 1, 28, 28, device="cuda")
     ms, kern = gpu_time(m, x)
@@ -84,28 +92,30 @@ for name, kw, batch in (("dgcspn_28x28_c8", dict(n_batch=8, sum_channels=8, dept
     cpu = None if NO_CPU else cpu_time(dgc_oracle_fn(m), x, 256)
     report(name, batch, 784, ms, kern, cpu, ms_t * batch / 8192)
 
-m = RealNVP1d(3072, n_flows=8, depth=2, units=512).cuda().eval()
-with torch.no_grad():
-    for n_, p in m.named_parameters():
-        if "scale_act" in n_:
-            p.fill_(0.5)
-x = torch.rand(16384, 3072, device="cuda")
-ms, kern = gpu_time(m, x)
-ms_t, _ = gpu_time(m, x, steps=3, grad=True)
-cpu = None
-if not NO_CPU:
-    from oracle.flows_oracle import flow1d_log_prob
-    st = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-    cpu = cpu_time(lambda t: flow1d_log_prob(t, st, "RealNVP1d", dict(in_features=3072))[0], x, 2048)
-report("realnvp1d_3072_8flows", 16384, 3072, ms, kern, cpu, ms_t)
+if want("realnvp1d_3072_8flows"):
+    m = RealNVP1d(3072, n_flows=8, depth=2, units=512).cuda().eval()
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if "scale_act" in n_:
+                p.fill_(0.5)
+    x = torch.rand(16384, 3072, device="cuda")
+    ms, kern = gpu_time(m, x)
+    ms_t, _ = gpu_time(m, x, steps=3, grad=True)
+    cpu = None
+    if not NO_CPU:
+        from oracle.flows_oracle import flow1d_log_prob
+        st = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        cpu = cpu_time(lambda t: flow1d_log_prob(t, st, "RealNVP1d", dict(in_features=3072))[0], x, 2048)
+    report("realnvp1d_3072_8flows", 16384, 3072, ms, kern, cpu, ms_t)
 
-m = BernoulliRatSpn(15, rg_depth=3, rg_repetitions=4, rg_batch=4, rg_sum=2, random_state=42).cuda().eval()
-x = ((torch.arange(2 ** 15).unsqueeze(1) >> torch.arange(14, -1, -1)) & 1).float().cuda()
-ms, kern = gpu_time(m, x)
-cpu = None
-if not NO_CPU:
-    from helpers import oracle_for
-    import param_gen as pg
-    orc, _ = oracle_for(pg.RATSPN_CASES["bern15"])
-    cpu = cpu_time(orc.log_prob, x, 32768)
-report("bernoulli_ratspn_15_all_states", 32768, 15, ms, kern, cpu)
+if want("bernoulli_ratspn_15_all_states"):
+    m = BernoulliRatSpn(15, rg_depth=3, rg_repetitions=4, rg_batch=4, rg_sum=2, random_state=42).cuda().eval()
+    x = ((torch.arange(2 ** 15).unsqueeze(1) >> torch.arange(14, -1, -1)) & 1).float().cuda()
+    ms, kern = gpu_time(m, x)
+    cpu = None
+    if not NO_CPU:
+        from helpers import oracle_for
+        import param_gen as pg
+        orc, _ = oracle_for(pg.RATSPN_CASES["bern15"])
+        cpu = cpu_time(orc.log_prob, x, 32768)
+    report("bernoulli_ratspn_15_all_states", 32768, 15, ms, kern, cpu)

@@ -60,16 +60,95 @@ def test_linear_out_of_range_rows_are_exact():
     assert torch.equal(out[399][fin], ref[399][fin])
 
 
-def test_realnvp1d_through_the_tensor_core_mlp(monkeypatch):
+def _perturbed_nvp(d, batch_norm, affine, seed=3):
     from deeprob_kit_b200.flows.models import RealNVP1d
-    torch.manual_seed(3)
-    model = RealNVP1d(256, n_flows=4, depth=2, units=128, batch_norm=True, affine=True).to(DEV).eval()
+    from deeprob_kit_b200.flows.utils import BatchNormLayer1d
+    torch.manual_seed(seed)
+    model = RealNVP1d(d, n_flows=4, depth=2, units=128, batch_norm=batch_norm, affine=affine).to(DEV).eval()
     with torch.no_grad():
         for p in model.parameters():
             p.add_(0.05 * torch.randn_like(p))
+        for m in model.modules():
+            if isinstance(m, BatchNormLayer1d):     # away from the identity, else the fused affine is untested
+                m.running_mean.add_(0.3 * torch.randn_like(m.running_mean))
+                m.running_var.mul_(torch.exp(0.3 * torch.randn_like(m.running_var)))
+    return model
+
+
+def test_realnvp1d_through_the_tensor_core_mlp(monkeypatch):
+    model = _perturbed_nvp(256, True, True)
     x = torch.rand(4096, 256, device=DEV)
-    monkeypatch.setenv("DPK_LINEAR_MMA", "1")
-    ll1 = model(x)
-    monkeypatch.setenv("DPK_LINEAR_MMA", "0")
-    ll0 = model(x)
+    monkeypatch.setenv("DPK_FLOW_COMPACT", "0")         # full-width conditioner with the mask folded into layer 1
+    with torch.no_grad():
+        monkeypatch.setenv("DPK_LINEAR_MMA", "1")
+        ll1 = model(x)
+        monkeypatch.setenv("DPK_LINEAR_MMA", "0")
+        ll0 = model(x)
     assert rel_err(ll1, ll0) < 1e-5
+    assert rel_err(ll0, model(x)) < 1e-6                # grad mode: stock modules
+
+
+@pytest.mark.parametrize("d,batch_norm,affine", [(256, True, True), (24, True, True), (36, True, True),
+                                                   (256, False, True), (64, True, False)])
+def test_realnvp1d_compact_inference(monkeypatch, d, batch_norm, affine):
+    """Inference fast path (live conditioner columns only, compact z, fused eval batch-norm) against the stock
+    module path: d = 24 gathers 12 live input columns, d = 36 has 18 (not a multiple of 4: mask folded instead)."""
+    model = _perturbed_nvp(d, batch_norm, affine, seed=d)
+    x = torch.rand(3000, d, device=DEV)
+    with torch.no_grad():
+        ll = model(x)
+        u, ildj = model.apply_backward(x)
+        xr, ldj = model.apply_forward(u)
+        monkeypatch.setenv("DPK_LINEAR_MMA", "0")
+        ll_ref = model(x)
+        u_ref, ildj_ref = model.apply_backward(x)
+        monkeypatch.delenv("DPK_LINEAR_MMA")
+    assert rel_err(ll, ll_ref) < 1e-5
+    assert float((u - u_ref).abs().max()) < 2e-5 * max(1.0, float(u_ref.abs().max()))
+    if affine:
+        assert float((ildj - ildj_ref).abs().max()) < 1e-4 * max(1.0, float(ildj_ref.abs().max()))
+        assert float((ildj + ldj).abs().max()) < 1e-3
+    assert float((xr - x).abs().max()) < 1e-4
+    # in-place parameter / running-statistic updates are picked up by the cached compact weights and affine
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.05)
+        for name, b in model.named_buffers():
+            if name.endswith("running_mean"):
+                b.add_(0.1)
+        ll2 = model(x)
+        monkeypatch.setenv("DPK_LINEAR_MMA", "0")
+        ll2_ref = model(x)
+    assert rel_err(ll2, ll2_ref) < 1e-5
+    assert rel_err(ll2, ll) > 1e-4
+
+
+def test_compact_coupling_entry_matches_plain_layout():
+    """dpk_coupling_forward_compact against dpk_coupling_forward on the scattered z, both directions."""
+    import ctypes
+    from deeprob_kit_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(11)
+    batch, n = 257, 40
+    inv = (torch.arange(n, device=DEV) % 3 != 0).float()
+    live = torch.nonzero(inv).reshape(-1)
+    zc = torch.randn(batch, 2 * live.numel(), device=DEV, generator=g)
+    z = torch.randn(batch, 2 * n, device=DEV, generator=g)          # dead columns hold garbage on purpose
+    z[:, live] = zc[:, :live.numel()]
+    z[:, n + live] = zc[:, live.numel():]
+    zmap = torch.zeros(n, dtype=torch.int32, device=DEV)
+    zmap[live] = torch.arange(live.numel(), dtype=torch.int32, device=DEV)
+    x = torch.randn(batch, n, device=DEV, generator=g)
+    w = torch.tensor([0.7], device=DEV)
+    pa = torch.rand(n, device=DEV, generator=g) + 0.5
+    pc = torch.randn(n, device=DEV, generator=g)
+    for direction in (0, 1):
+        ref, ref_ldj = _engine.coupling(x, z, w, inv, n, 0, True, direction, 1)
+        out = torch.empty_like(x)
+        ldj = torch.zeros(batch, device=DEV)
+        d = _engine._coupling_desc(batch, n, True, direction, w, 1, n, zc.shape[1], inv)
+        rc = _lib.lib().dpk_coupling_forward_compact(
+            ctypes.byref(d), _engine._ptr(x), _engine._ptr(zc), _engine._ptr(zmap), live.numel(), _engine._ptr(pa),
+            _engine._ptr(pc), ctypes.c_float(0.25), _engine._ptr(out), n, _engine._ptr(ldj), _engine._stream(x.device))
+        _lib.check(rc, "dpk_coupling_forward_compact")
+        assert float((out - (ref * pa + pc)).abs().max()) < 1e-5
+        assert float((ldj - (ref_ldj + 0.25)).abs().max()) < 1e-5
