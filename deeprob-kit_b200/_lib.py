@@ -142,7 +142,7 @@ SIGNATURES = {
     "dpk_dgc_root_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "dpk_coupling_forward": (ctypes.c_int, [ctypes.POINTER(CouplingDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dpk_coupling_forward_compact": (ctypes.c_int, [ctypes.POINTER(CouplingDesc), c_vp, c_vp, c_vp, c_i32, c_vp, c_vp,
-                                                    ctypes.c_float, c_vp, c_i64, c_vp, c_vp]),
+                                                    ctypes.c_float, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dpk_coupling_backward": (ctypes.c_int, [ctypes.POINTER(CouplingDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64,
                                              c_vp, c_i64, c_vp, c_vp]),
     "dpk_feature_reduce": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),

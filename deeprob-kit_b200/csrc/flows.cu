@@ -43,6 +43,7 @@ struct CouplingArgs {
   int N, w_count, w_inner, affine, direction;  // direction 0: u = (x - t) * exp(-s), ldj -= sum s ; 1: x = u * exp(s) + t, ldj += sum s
   const int* zmap; int z_half;         // compact conditioner output (forward only): column of element e, offset of the s half
   const float* post_scale; const float* post_shift; float post_ldj;  // fused per-feature affine after the coupling (eval batch-norm)
+  float* side; int64_t side_stride;    // optional compact copy of the transformed elements: side[b][zmap[e]] = out[b][e]
   int vec4;
 };
 
@@ -83,6 +84,13 @@ __global__ void __launch_bounds__(256) coupling_fwd_kernel(const CouplingArgs a)
           r.z = fmaf(r.z, pa.z, pc.z); r.w = fmaf(r.w, pa.w, pc.w);
         }
         *reinterpret_cast<float4*>(orow + e) = r;
+        if (a.side) {
+          float* sr = a.side + b * a.side_stride;
+          if (m.x != 0.f) sr[__ldg(a.zmap + e)] = r.x;
+          if (m.y != 0.f) sr[__ldg(a.zmap + e + 1)] = r.y;
+          if (m.z != 0.f) sr[__ldg(a.zmap + e + 2)] = r.z;
+          if (m.w != 0.f) sr[__ldg(a.zmap + e + 3)] = r.w;
+        }
       }
     } else {
       for (int e = threadIdx.x; e < a.N; e += 256) {
@@ -90,6 +98,7 @@ __global__ void __launch_bounds__(256) coupling_fwd_kernel(const CouplingArgs a)
         float r = coupling_elem(a, zr, e, m, xr[e], acc);
         if (a.post_scale) r = fmaf(r, __ldg(a.post_scale + e), __ldg(a.post_shift + e));
         orow[e] = r;
+        if (a.side && m != 0.f) a.side[b * a.side_stride + __ldg(a.zmap + e)] = r;
       }
     }
     if (a.ldj) {
@@ -302,7 +311,7 @@ static int fill_coupling(CouplingArgs* a, const dpk_coupling_desc* d, const floa
   a->x = x; a->x_stride = d->x_stride; a->z = z; a->z_stride = d->z_stride; a->inv_mask = d->inv_mask;
   a->w = d->scale_weight; a->out = nullptr; a->out_stride = 0; a->ldj = nullptr; a->B = d->batch; a->N = d->features;
   a->w_count = d->w_count; a->w_inner = d->w_inner; a->affine = d->affine; a->direction = d->direction;
-  a->zmap = nullptr; a->z_half = d->features; a->post_scale = a->post_shift = nullptr; a->post_ldj = 0.f; a->vec4 = 0;
+  a->zmap = nullptr; a->z_half = d->features; a->post_scale = a->post_shift = nullptr; a->post_ldj = 0.f; a->vec4 = 0; a->side = nullptr; a->side_stride = 0;
   return DPK_OK;
 }
 
@@ -335,17 +344,19 @@ extern "C" int dpk_coupling_forward(const dpk_coupling_desc* desc, const float* 
 extern "C" int dpk_coupling_forward_compact(const dpk_coupling_desc* desc, const float* x, const float* z,
                                             const int32_t* z_index, int32_t z_half, const float* post_scale,
                                             const float* post_shift, float post_log_det, float* out,
-                                            int64_t out_stride, float* log_det, void* stream) {
+                                            int64_t out_stride, float* live_out, float* log_det, void* stream) {
   CouplingArgs a;
   int rc = fill_coupling(&a, desc, x, z);
   if (rc) return rc;
   if ((post_scale == nullptr) != (post_shift == nullptr)) return set_error(DPK_E_ARG, "coupling: post affine needs scale and shift");
   if (z_index && (!desc->inv_mask || z_half <= 0)) return set_error(DPK_E_ARG, "coupling: compact z needs inv_mask and z_half");
   if (post_log_det != 0.f && !log_det) return set_error(DPK_E_ARG, "coupling: post log-det without accumulator");
+  if (live_out && !z_index) return set_error(DPK_E_ARG, "coupling: live_out needs z_index");
   if (a.B == 0) return DPK_OK;
   a.zmap = z_index;
   if (z_index) a.z_half = z_half;
   a.post_scale = post_scale; a.post_shift = post_shift; a.post_ldj = post_log_det;
+  a.side = live_out; a.side_stride = z_half;
   return launch_coupling_fwd(a, out, out_stride, log_det, stream);
 }
 

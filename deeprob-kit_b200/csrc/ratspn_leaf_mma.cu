@@ -52,7 +52,7 @@ constexpr int kImg = kMmaTileN * kMmaKB * 2;  // 16 KB: [256 rows][64 B] fp16, 6
 constexpr int kStage = 4 * kImg;              // A hi | A lo | B hi | B lo
 constexpr int kThreads = 576;
 constexpr int kEpiThread0 = 320;              // first epilogue thread (warp 10)
-constexpr uint32_t kSpinLimit = 1u << 26;     // bounded waits (seconds): a broken pipeline traps instead of hanging
+constexpr uint32_t kSpinLimit = 1u << 20;     // bounded waits (a few seconds): a broken pipeline traps instead of hanging
 
 struct LeafMmaArgs {
   const float* x;
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   uint64_t* tfull = bars + 2 * kMmaStages;   // accumulators of the unit complete
   uint64_t* tempty = tfull + 1;              // epilogue drained the accumulators
   uint64_t* sfull = tempty + 1;              // [kSchedSlots] unit index published
-  int* sched_s = reinterpret_cast<int*>(sfull + kSchedSlots);
+  uint64_t* sfree = sfull + kSchedSlots;     // [kSchedSlots] conversion-only launch: the 8 feeder warps have read the slot
+  int* sched_s = reinterpret_cast<int*>(sfree + kSchedSlots);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_s + kSchedSlots);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // the Gaussian PREP launch and the main launch run GEMMs; the Bernoulli PREP launch only converts
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     for (int s = 0; s < kMmaStages; ++s) { mbar_init(full + s, 9); mbar_init(empty + s, 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 8);
-    for (int s = 0; s < kSchedSlots; ++s) mbar_init(sfull + s, 1);
+    for (int s = 0; s < kSchedSlots; ++s) { mbar_init(sfull + s, 1); mbar_init(sfree + s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -227,6 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     int stage = 0; uint32_t phase = 0;
     for (int it = 0;; ++it) {
       int u = 0;
+      // A GEMM launch is throttled by the stage ring below.  A conversion-only launch has no such back-pressure:
+      // without this wait a fast scheduler would run around the unit ring and overwrite entries nobody has read.
+      if (!tensor && it >= kSchedSlots)
+        mbar_wait(sfree + (it & (kSchedSlots - 1)), (uint32_t)(it / kSchedSlots - 1) & 1u);
       if (lane == 0) {
         u = atomicAdd(a.unit_counter + (PREP ? 0 : 1), 1);
         if (u >= n_units) u = -1;
@@ -340,6 +345,10 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       if (++stage == kMmaStages) { stage = 0; phase ^= 1u; }
     };
     for (int it = 0; next_unit(it, &m, &j); ++it) {
+      if (!tensor) {                              // slot read by every lane: hand it back to the scheduler
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfree + (it & (kSchedSlots - 1)));
+      }
       unsigned char* gimg = a.aimg + (size_t)m * a.KBn * (2 * kImg);
       const int kb0 = (j >> 16) * a.kchunk, kb1 = min(a.KBn, kb0 + a.kchunk);
       j &= 0xffff;
@@ -1011,13 +1020,21 @@ extern "C" int dpk_linear_forward(const float* x, const float* weight, const flo
   }
   DPK_CUDA_TRY(cudaMemsetAsync(flg, 0, ((size_t)p.Bp / 32 + 3) * 4, st));
   const int cap = sm_count();
-  const int grid_prep = std::min(cap, a.nM), grid_main = std::min(cap, a.nM * a.nW);
+  // the PREP launch only converts here (no x^2 GEMM): cut every M tile into K chunks so that a batch of a few
+  // thousand rows (64 M tiles at 16 384) still gives every SM several units to stream
+  LeafMmaArgs ap = a;
+  if (a.nM < 4 * cap) {
+    const int nc = std::min(a.KBn, (int)ceil_div(4 * cap, a.nM));
+    ap.kchunk = std::max(env_int("DPK_LINEAR_PREP_KC", 2), (int)ceil_div(a.KBn, nc));
+    ap.nC = (int)ceil_div(a.KBn, ap.kchunk);
+  }
+  const int grid_prep = std::min(cap, ap.nM * ap.nC), grid_main = std::min(cap, a.nM * a.nW);
   const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope prof(CAT_GEMM, st, 3);
-    ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(a);
+    ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(ap);
     DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<prep> (linear)");
     ratspn_leaf_mma_kernel<false><<<grid_main, kThreads, smem, st>>>(a);
     DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main> (linear)");

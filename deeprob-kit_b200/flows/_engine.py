@@ -375,9 +375,20 @@ def coupling1d_infer(layer, x, direction, bn=None):
     if live_out.numel() == 0:
         return None
     first, last = plan[0][0], plan[-1][0]
-    # first layer: gathered live columns when the mask is 0/1 and their count keeps 16-byte rows, else the fold
+    # first layer: live input columns when the mask is 0/1 and their count keeps 16-byte rows, else the fold.  The
+    # previous coupling of the chain leaves exactly these columns next to its output (live_out of the C entry)
+    # when its transformed set is this layer's conditioner input (alternating masks); otherwise they are gathered.
     if cache["binary"] and live_in.numel() and live_in.numel() % 4 == 0:
-        h = x.index_select(1, live_in)
+        h = None
+        hint = getattr(x, "_dpk_live", None)
+        if hint is not None and hint[2] == x._version and hint[1].shape[0] == batch:
+            same = cache.setdefault("hint_ok", {})
+            if hint[0].data_ptr() not in same:
+                same[hint[0].data_ptr()] = hint[0].shape == live_in.shape and bool(torch.equal(hint[0], live_in))
+            if same[hint[0].data_ptr()]:
+                h = hint[1]
+        if h is None:
+            h = x.index_select(1, live_in)
         w0 = _derived(cache, "w_first", (first.weight,), lambda: first.weight.detach().index_select(1, live_in))
     else:
         h = x
@@ -398,10 +409,15 @@ def coupling1d_infer(layer, x, direction, bn=None):
         post_a, post_c, post_ldj = eval_batch_norm_affine(bn)
     out = torch.empty_like(x)
     ldj = torch.zeros(batch, dtype=torch.float32, device=x.device)
+    side = None
+    if direction == 0 and os.environ.get("DPK_FLOW_SIDE", "1") != "0":
+        side = torch.empty(batch, live_out.numel(), dtype=torch.float32, device=x.device)
     d = _coupling_desc(batch, n, layer.affine, direction, w, 1, n, z.shape[1], layer.inv_mask)
     with torch.cuda.device(x.device):
         rc = _lib.lib().dpk_coupling_forward_compact(
             ctypes.byref(d), _ptr(x), _ptr(z), _ptr(cache["zmap"]), live_out.numel(), _ptr(post_a), _ptr(post_c),
-            ctypes.c_float(post_ldj), _ptr(out), n, _ptr(ldj), _stream(x.device))
+            ctypes.c_float(post_ldj), _ptr(out), n, _ptr(side), _ptr(ldj), _stream(x.device))
     _lib.check(rc, "dpk_coupling_forward_compact")
+    if side is not None:
+        out._dpk_live = (live_out, side, out._version)      # valid for this tensor object until it is written to
     return out, ldj

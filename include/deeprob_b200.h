@@ -211,11 +211,14 @@ int dpk_coupling_forward(const dpk_coupling_desc* desc, const float* x, const fl
  * reach the result because coupling.py:79-80 multiplies t and s by inv_mask): z rows hold [t_live | s_live],
  * z_index[e] = column of element e (ignored where inv_mask[e] == 0), z_half = offset of the s half; z_index NULL =
  * the plain layout.  post_scale/post_shift (N, or both NULL) apply the following eval-mode BatchNormLayer1d
- * (flows/utils.py:118-139) as out = out*post_scale + post_shift and add post_log_det to every log_det entry. */
+ * (flows/utils.py:118-139) as out = out*post_scale + post_shift and add post_log_det to every log_det entry.
+ * live_out (B, z_half; may be NULL, needs z_index) additionally receives the transformed elements alone,
+ * live_out[b][z_index[e]] = out[b][e]: with alternating masks these are exactly the columns the next coupling's
+ * conditioner reads, which saves its gather. */
 int dpk_coupling_forward_compact(const dpk_coupling_desc* desc, const float* x, const float* z,
                                  const int32_t* z_index, int32_t z_half, const float* post_scale,
                                  const float* post_shift, float post_log_det, float* out, int64_t out_stride,
-                                 float* log_det, void* stream);
+                                 float* live_out, float* log_det, void* stream);
 /* grad_x (may be NULL) and grad_z are overwritten; grad_scale_weight (w_count, may be NULL) is accumulated into */
 int dpk_coupling_backward(const dpk_coupling_desc* desc, const float* x, const float* z, const float* grad_out,
                           int64_t grad_out_stride, const float* grad_log_det, float* grad_x, int64_t grad_x_stride,

@@ -99,6 +99,9 @@ def test_realnvp1d_compact_inference(monkeypatch, d, batch_norm, affine):
         ll = model(x)
         u, ildj = model.apply_backward(x)
         xr, ldj = model.apply_forward(u)
+        monkeypatch.setenv("DPK_FLOW_SIDE", "0")            # gather the live columns instead of the chained side output
+        assert torch.equal(model(x), ll)
+        monkeypatch.delenv("DPK_FLOW_SIDE")
         monkeypatch.setenv("DPK_LINEAR_MMA", "0")
         ll_ref = model(x)
         u_ref, ildj_ref = model.apply_backward(x)
@@ -144,11 +147,14 @@ def test_compact_coupling_entry_matches_plain_layout():
     for direction in (0, 1):
         ref, ref_ldj = _engine.coupling(x, z, w, inv, n, 0, True, direction, 1)
         out = torch.empty_like(x)
+        side = torch.full((batch, live.numel()), float("nan"), device=DEV)
         ldj = torch.zeros(batch, device=DEV)
         d = _engine._coupling_desc(batch, n, True, direction, w, 1, n, zc.shape[1], inv)
         rc = _lib.lib().dpk_coupling_forward_compact(
             ctypes.byref(d), _engine._ptr(x), _engine._ptr(zc), _engine._ptr(zmap), live.numel(), _engine._ptr(pa),
-            _engine._ptr(pc), ctypes.c_float(0.25), _engine._ptr(out), n, _engine._ptr(ldj), _engine._stream(x.device))
+            _engine._ptr(pc), ctypes.c_float(0.25), _engine._ptr(out), n, _engine._ptr(side), _engine._ptr(ldj),
+            _engine._stream(x.device))
         _lib.check(rc, "dpk_coupling_forward_compact")
         assert float((out - (ref * pa + pc)).abs().max()) < 1e-5
+        assert torch.equal(side, out[:, live])
         assert float((ldj - (ref_ldj + 0.25)).abs().max()) < 1e-5
