@@ -14,9 +14,16 @@
 // running log-det vector in the same kernel.  The conditioner networks (MLP / conv) stay library calls.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dpk {
+
+static inline int flow_env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v && *v ? std::atoi(v) : dflt;
+}
 
 __device__ __forceinline__ float block_sum_256(float v, float* red) {
   v = warp_sum(v);
@@ -68,8 +75,9 @@ __global__ void __launch_bounds__(256) coupling_fwd_kernel(const CouplingArgs a)
     float acc = 0.f;
     if (a.vec4) {
       // 16-byte loads/stores of x, mask, out (and of the fused batch-norm affine); z through scalar loads
+      float* sr = a.side ? a.side + b * a.side_stride : nullptr;
       for (int e = threadIdx.x * 4; e < a.N; e += 1024) {
-        const float4 xv = *reinterpret_cast<const float4*>(xr + e);
+        const float4 xv = __ldcs(reinterpret_cast<const float4*>(xr + e));
         float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
         if (a.inv_mask) m = __ldg(reinterpret_cast<const float4*>(a.inv_mask + e));
         float4 r;
@@ -84,8 +92,7 @@ __global__ void __launch_bounds__(256) coupling_fwd_kernel(const CouplingArgs a)
           r.z = fmaf(r.z, pa.z, pc.z); r.w = fmaf(r.w, pa.w, pc.w);
         }
         *reinterpret_cast<float4*>(orow + e) = r;
-        if (a.side) {
-          float* sr = a.side + b * a.side_stride;
+        if (sr) {
           if (m.x != 0.f) sr[__ldg(a.zmap + e)] = r.x;
           if (m.y != 0.f) sr[__ldg(a.zmap + e + 1)] = r.y;
           if (m.z != 0.f) sr[__ldg(a.zmap + e + 2)] = r.z;
@@ -290,6 +297,33 @@ __global__ void __launch_bounds__(256) normal_prior_fwd_kernel(const float* __re
   }
 }
 
+// N % 4 == 0 and 16-byte aligned rows: one warp per row, 16-byte loads
+__global__ void __launch_bounds__(256) normal_prior_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ loc,
+                                                                   const float* __restrict__ scale,
+                                                                   const float* __restrict__ ildj, float* __restrict__ out,
+                                                                   int64_t B, int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
+  for (int64_t b = w0; b < B; b += nw) {
+    const float* zr = z + b * N;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int e = lane * 4; e < N; e += 128) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(zr + e));
+      float4 sg = make_float4(1.f, 1.f, 1.f, 1.f), lc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (scale) sg = __ldg(reinterpret_cast<const float4*>(scale + e));
+      if (loc) lc = __ldg(reinterpret_cast<const float4*>(loc + e));
+      const float t0 = (v.x - lc.x) / sg.x, t1 = (v.y - lc.y) / sg.y, t2 = (v.z - lc.z) / sg.z, t3 = (v.w - lc.w) / sg.w;
+      acc += -0.5f * t0 * t0 - (scale ? logf(sg.x) : 0.f) - kLogSqrt2Pi;
+      acc += -0.5f * t1 * t1 - (scale ? logf(sg.y) : 0.f) - kLogSqrt2Pi;
+      acc += -0.5f * t2 * t2 - (scale ? logf(sg.z) : 0.f) - kLogSqrt2Pi;
+      acc += -0.5f * t3 * t3 - (scale ? logf(sg.w) : 0.f) - kLogSqrt2Pi;
+    }
+    const float tot = warp_sum(acc);
+    if (lane == 0) out[b] = tot + (ildj ? ildj[b] : 0.f);
+  }
+}
+
 __global__ void normal_prior_bwd_kernel(const float* __restrict__ z, const float* __restrict__ loc,
                                         const float* __restrict__ scale, const float* __restrict__ gout,
                                         float* __restrict__ gz, int64_t B, int N) {
@@ -444,6 +478,13 @@ extern "C" int dpk_normal_prior_forward(const float* z, const float* loc, const 
   if (!z || !out) return set_error(DPK_E_ARG, "normal_prior: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(CAT_FLOW, st);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (flow_env_int("DPK_PRIOR_WARP", 1) && features % 4 == 0 && features >= 128 && al16(z) && al16(loc) && al16(scale)) {
+    normal_prior_fwd_vec_kernel<<<(unsigned)std::min<int64_t>(ceil_div(batch, 8), (int64_t)sm_count() * 16), 256, 0, st>>>(
+        z, loc, scale, inv_log_det, out, batch, features);
+    DPK_LAUNCH_CHECK("normal_prior_fwd_vec_kernel");
+    return DPK_OK;
+  }
   normal_prior_fwd_kernel<<<sample_grid(batch), 256, 0, st>>>(z, loc, scale, inv_log_det, out, batch, features);
   DPK_LAUNCH_CHECK("normal_prior_fwd_kernel");
   return DPK_OK;
