@@ -81,16 +81,20 @@ __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_kernel(const Ei
     for (int s = 0; s < ST; ++s) {
       const int row = tid + s * kBwdThreads;
       const int64_t b = base + row;
+      float gq[OC];
+#pragma unroll
+      for (int o = 0; o < OC; ++o) {   // loads first (clamped addresses, no control flow between them)
+        const int oo = min(oc * OC + o, a.O - 1);
+        const int64_t bc = min(b, a.B - 1);
+        const size_t at = a.root ? (size_t)bc * a.O + oo : ((size_t)p * a.O + oo) * a.Bp + bc;
+        q[s][o] = a.y[at];
+        gq[o] = a.gy ? a.gy[at] : 1.f;
+      }
 #pragma unroll
       for (int o = 0; o < OC; ++o) {
-        const int oo = oc * OC + o;
-        float qv = 0.f;
-        if (oo < a.O && b < a.B) {
-          const size_t at = a.root ? (size_t)b * a.O + oo : ((size_t)p * a.O + oo) * a.Bp + b;
-          const float yv = a.y[at];
-          const float g = a.gy ? a.gy[at] : 1.f;
-          if (fabsf(yv) <= FLT_MAX && g != 0.f) qv = g * __expf(fminf(ml[s] + mr[s] - yv, 80.f));
-        }
+        const float yv = q[s][o], g = gq[o];
+        const bool live = oc * OC + o < a.O && b < a.B && fabsf(yv) <= FLT_MAX && g != 0.f;
+        const float qv = live ? g * __expf(fminf(ml[s] + mr[s] - yv, 80.f)) : 0.f;
         q[s][o] = qv;
         q_sm[row * QS + o] = qv;
       }
@@ -207,16 +211,33 @@ __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_reg_kernel(cons
     reinterpret_cast<float2*>(wsm)[t] = __ldg(reinterpret_cast<const float2*>(wp) + t);
 
   float elr[ST][KIN], err[ST][KIN], gr[ST][KIN], q[ST][OC];
+  // every global load of the thread is issued before the first use (clamped addresses instead of predicated
+  // loads, no control flow in between): one memory latency per CTA instead of one per output
+  float gq[ST][OC];
+#pragma unroll
+  for (int s = 0; s < ST; ++s) {
+    const int64_t b = min(base + tid + s * kBwdThreads, a.B - 1);
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+      elr[s][k] = lin[(size_t)k * a.Bp + b];
+      err[s][k] = rin[(size_t)k * a.Bp + b];
+    }
+#pragma unroll
+    for (int o = 0; o < OC; ++o) {
+      const int oc = min(o, a.O - 1);
+      const size_t at = a.root ? (size_t)b * a.O + oc : ((size_t)p * a.O + oc) * a.Bp + b;
+      q[s][o] = a.y[at];
+      gq[s][o] = a.gy ? a.gy[at] : 1.f;
+    }
+  }
 #pragma unroll
   for (int s = 0; s < ST; ++s) {
     const int row = tid + s * kBwdThreads;
-    const int64_t b = base + row;
-    const bool inb = b < a.B;
+    const bool inb = base + row < a.B;
     float vl = -INFINITY, vr = -INFINITY;
 #pragma unroll
     for (int k = 0; k < KIN; ++k) {
-      elr[s][k] = inb ? lin[(size_t)k * a.Bp + b] : 0.f;
-      err[s][k] = inb ? rin[(size_t)k * a.Bp + b] : 0.f;
+      if (!inb) { elr[s][k] = 0.f; err[s][k] = 0.f; }
       vl = fmaxf(vl, elr[s][k]); vr = fmaxf(vr, err[s][k]);
     }
     const float ml = (fabsf(vl) <= FLT_MAX) ? vl : 0.f;
@@ -231,13 +252,9 @@ __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_reg_kernel(cons
     }
 #pragma unroll
     for (int o = 0; o < OC; ++o) {
-      float qv = 0.f;
-      if (o < a.O && inb) {
-        const size_t at = a.root ? (size_t)b * a.O + o : ((size_t)p * a.O + o) * a.Bp + b;
-        const float yv = a.y[at];
-        const float g = a.gy ? a.gy[at] : 1.f;
-        if (fabsf(yv) <= FLT_MAX && g != 0.f) qv = g * __expf(fminf(ml + mr - yv, 80.f));
-      }
+      const float yv = q[s][o], g = gq[s][o];
+      const bool live = o < a.O && inb && fabsf(yv) <= FLT_MAX && g != 0.f;
+      const float qv = live ? g * __expf(fminf(ml + mr - yv, 80.f)) : 0.f;
       q[s][o] = qv;
       q_sm[row * QS + o] = qv;
     }
