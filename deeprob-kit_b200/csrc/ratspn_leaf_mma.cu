@@ -162,7 +162,9 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 
 constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units behind the scheduler (3 stages + 2)
 
-template <bool PREP>
+// GEN (PREP launch of a general Gaussian only) is a template parameter: as a run-time branch in the conversion loop
+// it cost the unit-scale path 19 % (0.135 -> 0.160 ms) through the register allocation of that loop.
+template <bool PREP, bool GEN = false>
 __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const LeafMmaArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         const int c8 = lane & 7, rsub = lane >> 3;
         const bool first = (j == 0);            // splits x for the whole M tile (K chunk) and checks its range
         const bool sq = a.quad != 0;            // feeds the x^2 GEMM of this unit through shared memory
-        const bool gen = a.gen != 0;            // x^2 images to the global scratch (second half of the K blocks)
+        constexpr bool gen = GEN;               // x^2 images to the global scratch (second half of the K blocks)
         const int KBh = gen ? a.KBn / 2 : a.KBn; // K blocks of x itself
         const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
         auto split = [](const float4& v, uint2* hv, uint2* lv) {
@@ -870,7 +872,12 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope prof(CAT_LEAF_MMA_PREP, st);
-    ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(a);
+    if (a.gen) {
+      DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ratspn_leaf_mma_kernel<true, true><<<grid_prep, kThreads, smem, st>>>(a);
+    } else {
+      ratspn_leaf_mma_kernel<true><<<grid_prep, kThreads, smem, st>>>(a);
+    }
     DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<prep>");
   }
   {
