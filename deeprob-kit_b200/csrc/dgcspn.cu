@@ -387,18 +387,24 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
         wsm[(i * OC + o) * 128 + lane_px] = (live && o0 + o < O) ? __ldg(wsoft + ((size_t)(o0 + o) * IC + i) * HW + hw) : 0.f;
     __syncthreads();
     if (!live) continue;
-    for (int64_t bb = b0; bb < b1; bb += kPsNB) {
+    // 32-bit element offsets against CTA-uniform slice bases (the host keeps a slice below 2^31 elements): one
+    // integer add per load instead of a 64-bit address chain -- the kernel is instruction bound, not HBM bound
+    const float* __restrict__ xs = x + (size_t)b0 * IC * IHW;
+    float* __restrict__ os = out + (size_t)b0 * O * HW;
+    const unsigned nb = (unsigned)(b1 - b0);
+    const unsigned sIHW = (unsigned)IHW, sHW = (unsigned)HW;
+    for (unsigned rb = 0; rb < nb; rb += kPsNB) {
       float pv[kPsNB][IC], m[kPsNB];
 #pragma unroll
       for (int s = 0; s < kPsNB; ++s) {
-        const float* xb = x + (size_t)min((long long)(bb + s), (long long)(b1 - 1)) * IC * IHW;   // clamped: loads unconditional
+        const unsigned xb = min(rb + s, nb - 1) * (IC * sIHW);   // clamped: loads unconditional
 #pragma unroll
         for (int i = 0; i < IC; ++i) {
-          const float* xc = xb + (size_t)i * IHW;
+          const unsigned xc = xb + i * sIHW;
           float v = 0.f;                         // zero padding = log 1
 #pragma unroll
           for (int tap = 0; tap < 4; ++tap)
-            if (ok[tap]) v += xc[off[tap]];
+            if (ok[tap]) v += xs[xc + off[tap]];
           pv[s][i] = v;
         }
       }
@@ -426,29 +432,60 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
           for (int o = 0; o < OC; ++o) acc[s][o] = fmaf(w[o], e, acc[s][o]);
         }
       }
+      // common case first, without a branch per output; samples with an out-of-range sum are redone exactly
+      bool redo = false;
 #pragma unroll
       for (int s = 0; s < kPsNB; ++s) {
-        if (bb + s >= b1) continue;
+        if (rb + s >= nb) continue;
+        const unsigned ob = ((rb + s) * (unsigned)O + o0) * sHW + hw;
 #pragma unroll
         for (int o = 0; o < OC; ++o) {
           if (o0 + o >= O) continue;
-          float y;
-          if (acc[s][o] >= 1e-18f && acc[s][o] <= FLT_MAX) {
-            y = m[s] + __logf(acc[s][o]);
-          } else {  // exact log-domain evaluation
+          redo |= !(acc[s][o] >= 1e-18f && acc[s][o] <= FLT_MAX);
+          os[ob + o * sHW] = m[s] + __logf(acc[s][o]);
+        }
+      }
+      if (redo) {
+#pragma unroll 1
+        for (int s = 0; s < kPsNB; ++s) {
+          if (rb + s >= nb) continue;
+#pragma unroll 1
+          for (int o = 0; o < OC; ++o) {
+            if (o0 + o >= O) continue;
+            float av = 0.f;                      // runtime-indexed registers would go to local memory: select
+#pragma unroll
+            for (int s2 = 0; s2 < kPsNB; ++s2)
+#pragma unroll
+              for (int o2 = 0; o2 < OC; ++o2)
+                if (s2 == s && o2 == o) av = acc[s2][o2];
+            if (av >= 1e-18f && av <= FLT_MAX) continue;
+            // exact log-domain evaluation
             float mm = -INFINITY;
+            for (int i = 0; i < IC; ++i) {
+              float pvi = 0.f;
 #pragma unroll
-            for (int i = 0; i < IC; ++i) mm = fmaxf(mm, pv[s][i] + wlog[((size_t)(o0 + o) * IC + i) * HW + hw]);
-            if (!(fabsf(mm) <= FLT_MAX)) {
-              y = mm;
-            } else {
+              for (int s2 = 0; s2 < kPsNB; ++s2)
+#pragma unroll
+                for (int i2 = 0; i2 < IC; ++i2)
+                  if (s2 == s && i2 == i) pvi = pv[s2][i2];
+              mm = fmaxf(mm, pvi + wlog[((size_t)(o0 + o) * IC + i) * HW + hw]);
+            }
+            float y = mm;
+            if (fabsf(mm) <= FLT_MAX) {
               float ss = 0.f;
+              for (int i = 0; i < IC; ++i) {
+                float pvi = 0.f;
 #pragma unroll
-              for (int i = 0; i < IC; ++i) ss += expf(pv[s][i] + wlog[((size_t)(o0 + o) * IC + i) * HW + hw] - mm);
+                for (int s2 = 0; s2 < kPsNB; ++s2)
+#pragma unroll
+                  for (int i2 = 0; i2 < IC; ++i2)
+                    if (s2 == s && i2 == i) pvi = pv[s2][i2];
+                ss += expf(pvi + wlog[((size_t)(o0 + o) * IC + i) * HW + hw] - mm);
+              }
               y = mm + logf(ss);
             }
+            os[((rb + s) * (unsigned)O + o0 + o) * sHW + hw] = y;
           }
-          out[((bb + s) * O + o0 + o) * HW + hw] = y;
         }
       }
     }
@@ -792,6 +829,9 @@ extern "C" int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const f
   const size_t smem = (size_t)I * OC * 128 * sizeof(float);
   const int64_t per = round_up(ceil_div(batch, std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)env_int_dgc("DPK_DGC_CTAS_PER_SM", 8) * sm_count(), bx)),
                                                                    std::max<int64_t>(1, batch / 64))), 4);
+  // the kernel addresses a slice with 32-bit element offsets
+  const int64_t row_elems = std::max<int64_t>((int64_t)I * d.H * d.W, (int64_t)out_channels * hw);
+  if (per * row_elems >= (int64_t(1) << 31)) return set_error(DPK_E_ARG, "dgc_prodsum: layer too large for one batch slice");
   dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
 #define DPK_PS(ic_, oc_)                                                                                            \
   {                                                                                                                 \

@@ -1,0 +1,22 @@
+"""Launch list of one DgcSpn((1,28,28), n_batch=8, sum_channels=8, depthwise=True) log-prob at batch 32768 (config 3):
+  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python profiles/prof_dgc.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT]
+import torch  # noqa: E402
+
+from deeprob_kit_b200.spn.models import DgcSpn  # noqa: E402
+
+torch.manual_seed(0)
+m = DgcSpn((1, 28, 28), n_batch=8, sum_channels=8, depthwise=True).cuda().eval()
+x = torch.randn(32768, 1, 28, 28, device="cuda")
+with torch.no_grad():
+    for _ in range(2):
+        m(x)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    m(x)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
