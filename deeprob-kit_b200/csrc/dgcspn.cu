@@ -44,6 +44,59 @@ __global__ void dgc_leaf_fwd_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// thread = pixel, CTA.y = batch slice: the (mu, 1/sigma, -log sigma - log sqrt(2 pi)) of KC components x CIN input
+// channels stay in registers over the slice, so a sample costs one load per channel, ~6 instructions per output and
+// one coalesced store per component (the per-plane kernel above redoes the division and the logarithm for every
+// element: ~40 instructions per output, 4x off the HBM time of its 0.87 GB).
+template <int CIN, int KC>
+__global__ void __launch_bounds__(128) dgc_leaf_fwd_px_kernel(const float* __restrict__ x, const float* __restrict__ loc,
+                                                              const float* __restrict__ scale, float* __restrict__ out,
+                                                              int64_t B, int K, int HW, int64_t per_slice) {
+  const int hw = blockIdx.x * 128 + threadIdx.x;
+  if (hw >= HW) return;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  const float* __restrict__ xs = x + (size_t)b0 * CIN * HW;
+  float* __restrict__ os = out + (size_t)b0 * K * HW;
+  const unsigned nb = (unsigned)(b1 - b0), sHW = (unsigned)HW;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    float mu[KC][CIN], inv[KC][CIN], lg[KC][CIN];
+#pragma unroll
+    for (int k = 0; k < KC; ++k)
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        const int pi = (min(k0 + k, K - 1) * CIN + c) * HW + hw;
+        const float sg = __ldg(scale + pi);
+        mu[k][c] = __ldg(loc + pi);
+        inv[k][c] = 1.0f / sg;
+        lg[k][c] = -logf(sg) - kLogSqrt2Pi;
+      }
+    constexpr int NB = 4;
+    for (unsigned rb = 0; rb < nb; rb += NB) {
+      float xv[NB][CIN];
+#pragma unroll
+      for (int s = 0; s < NB; ++s)
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) xv[s][c] = xs[(min(rb + s, nb - 1) * CIN + c) * sHW + hw];
+#pragma unroll
+      for (int s = 0; s < NB; ++s) {
+        if (rb + s >= nb) continue;
+        const unsigned ob = ((rb + s) * (unsigned)K + k0) * sHW + hw;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          if (k0 + k >= K) continue;
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            const float t = (xv[s][c] - mu[k][c]) * inv[k][c];
+            acc += nan_to_num(fmaf(-0.5f * t, t, lg[k][c]));
+          }
+          os[ob + k * sHW] = acc;
+        }
+      }
+    }
+  }
+}
+
 // gx[b,c,hw] = sum_k g * -(x-mu)/s^2   (zero where x is non-finite: nan_to_num'ed terms have no gradient)
 __global__ void dgc_leaf_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ loc,
                                       const float* __restrict__ scale, const float* __restrict__ g,
@@ -352,6 +405,22 @@ __global__ void __launch_bounds__(128) dgc_sum_fwd_smem_kernel(const float* __re
   }
 }
 
+__device__ float g_dgc_zero = 0.f;   // what a tap in the zero padding reads
+__device__ __forceinline__ float ld_nc_f32(unsigned long long addr) {
+  float v;
+  asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_f32(unsigned long long addr, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+// lg2.approx.ftz without the denormal prescaling of __logf: the caller has sums >= 1e-18 on this path
+__device__ __forceinline__ float lg2_fast(float v) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // Fused depthwise SpatialProductLayer + SpatialSumLayer (inference): the product output -- the largest tensor of
 // the model, written once and read once by the unfused pair -- never touches HBM.  thread = output pixel; the four
 // taps of every input channel are gathered straight from the product layer's input (lanes = consecutive pixels:
@@ -393,19 +462,31 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
     float* __restrict__ os = out + (size_t)b0 * O * HW;
     const unsigned nb = (unsigned)(b1 - b0);
     const unsigned sIHW = (unsigned)IHW, sHW = (unsigned)HW;
+    const bool all_out = o0 + OC <= O;
+    // Explicit 64-bit byte addresses, one per tap, stepped from plane to plane (a 64-bit add per load; left to the
+    // compiler every load re-derives its address from the kernel argument: six instructions).  A tap in the zero
+    // padding reads a zero word with step 0, so the loads need no predicate.
+    unsigned long long ta[4];
+    unsigned tstep[4], tsamp[4];
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      ta[tap] = ok[tap] ? (unsigned long long)(xs + off[tap]) : (unsigned long long)&g_dgc_zero;
+      tstep[tap] = ok[tap] ? sIHW * 4u : 0u;
+      tsamp[tap] = ok[tap] ? IC * sIHW * 4u : 0u;
+    }
     for (unsigned rb = 0; rb < nb; rb += kPsNB) {
       float pv[kPsNB][IC], m[kPsNB];
 #pragma unroll
       for (int s = 0; s < kPsNB; ++s) {
-        const unsigned xb = min(rb + s, nb - 1) * (IC * sIHW);   // clamped: loads unconditional
+        const unsigned sb = min(rb + s, nb - 1);   // clamped: loads unconditional
+        unsigned long long q0 = ta[0] + (unsigned long long)sb * tsamp[0];
+        unsigned long long q1 = ta[1] + (unsigned long long)sb * tsamp[1];
+        unsigned long long q2 = ta[2] + (unsigned long long)sb * tsamp[2];
+        unsigned long long q3 = ta[3] + (unsigned long long)sb * tsamp[3];
 #pragma unroll
         for (int i = 0; i < IC; ++i) {
-          const unsigned xc = xb + i * sIHW;
-          float v = 0.f;                         // zero padding = log 1
-#pragma unroll
-          for (int tap = 0; tap < 4; ++tap)
-            if (ok[tap]) v += xs[xc + off[tap]];
-          pv[s][i] = v;
+          pv[s][i] = (ld_nc_f32(q0) + ld_nc_f32(q1)) + (ld_nc_f32(q2) + ld_nc_f32(q3));   // zero padding = log 1
+          q0 += tstep[0]; q1 += tstep[1]; q2 += tstep[2]; q3 += tstep[3];
         }
       }
 #pragma unroll
@@ -432,19 +513,36 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
           for (int o = 0; o < OC; ++o) acc[s][o] = fmaf(w[o], e, acc[s][o]);
         }
       }
-      // common case first, without a branch per output; samples with an out-of-range sum are redone exactly
-      bool redo = false;
+      // common case first, without a branch per output; samples with an out-of-range sum are redone exactly.
+      // Range check of all sums at once: the minimum catches tiny / negative values, the total catches inf and NaN.
+      float amin = FLT_MAX, atot = 0.f;
+      if (all_out && rb + kPsNB <= nb) {          // whole group: no per-output conditions
 #pragma unroll
-      for (int s = 0; s < kPsNB; ++s) {
-        if (rb + s >= nb) continue;
-        const unsigned ob = ((rb + s) * (unsigned)O + o0) * sHW + hw;
+        for (int s = 0; s < kPsNB; ++s) {
+          unsigned long long op = (unsigned long long)(os + hw) + (unsigned long long)((rb + s) * (unsigned)O + o0) * (sHW * 4u);
 #pragma unroll
-        for (int o = 0; o < OC; ++o) {
-          if (o0 + o >= O) continue;
-          redo |= !(acc[s][o] >= 1e-18f && acc[s][o] <= FLT_MAX);
-          os[ob + o * sHW] = m[s] + __logf(acc[s][o]);
+          for (int o = 0; o < OC; ++o) {
+            amin = fminf(amin, acc[s][o]);
+            atot += acc[s][o];
+            st_f32(op, fmaf(lg2_fast(acc[s][o]), 0.6931471805599453f, m[s]));
+            op += sHW * 4u;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < kPsNB; ++s) {
+          if (rb + s >= nb) continue;
+          unsigned long long op = (unsigned long long)(os + hw) + (unsigned long long)((rb + s) * (unsigned)O + o0) * (sHW * 4u);
+#pragma unroll
+          for (int o = 0; o < OC; ++o) {
+            if (o0 + o >= O) continue;
+            amin = fminf(amin, acc[s][o]);
+            atot += acc[s][o];
+            st_f32(op + (unsigned long long)o * (sHW * 4u), fmaf(lg2_fast(acc[s][o]), 0.6931471805599453f, m[s]));
+          }
         }
       }
+      const bool redo = !(amin >= 1e-18f && atot <= FLT_MAX);
       if (redo) {
 #pragma unroll 1
         for (int s = 0; s < kPsNB; ++s) {
@@ -699,6 +797,17 @@ extern "C" int dpk_dgc_leaf_forward(const float* x, const float* loc, const floa
   if (!x || !loc || !scale || !out) return set_error(DPK_E_ARG, "dgc_leaf: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(CAT_DGC, st);
+  if ((in_channels == 1 || in_channels == 3) && env_int_dgc("DPK_DGC_LEAF_PX", 1)) {
+    const int64_t bx = ceil_div(hw, 128);
+    int64_t per = round_up(ceil_div(batch, std::max<int64_t>(1, ceil_div((int64_t)8 * sm_count(), bx))), 4);
+    const int64_t row = (int64_t)std::max(in_channels, out_channels) * hw;
+    per = std::max<int64_t>(4, std::min<int64_t>(per, ((int64_t(1) << 31) - 1) / row / 4 * 4));   // 32-bit offsets inside a slice
+    dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
+    if (in_channels == 1) dgc_leaf_fwd_px_kernel<1, 8><<<grid, 128, 0, st>>>(x, loc, scale, out, batch, out_channels, hw, per);
+    else dgc_leaf_fwd_px_kernel<3, 8><<<grid, 128, 0, st>>>(x, loc, scale, out, batch, out_channels, hw, per);
+    DPK_LAUNCH_CHECK("dgc_leaf_fwd_px_kernel");
+    return DPK_OK;
+  }
   dgc_leaf_fwd_kernel<<<plane_grid(batch * out_channels), 256, 0, st>>>(x, loc, scale, out, batch, in_channels,
                                                                                  out_channels, hw);
   DPK_LAUNCH_CHECK("dgc_leaf_fwd_kernel");
