@@ -102,8 +102,17 @@ def test_fused_product_sum_matches_layerwise(name, monkeypatch):
     cfg = pg.DGCSPN_CASES[name]
     model = dgc_product_model(cfg, DEV)
     x = pg.dgcspn_inputs(cfg)[0].to(DEV)
-    monkeypatch.setenv("DPK_DGC_FUSE", "1")
-    fused = model(x)
-    monkeypatch.setenv("DPK_DGC_FUSE", "0")
-    plain = model(x)
+    with torch.no_grad():      # the fused kernels carry no autograd node: they are used in inference only
+        monkeypatch.setenv("DPK_DGC_FUSE", "1")
+        fused = model(x)
+        monkeypatch.setenv("DPK_DGC_FUSE", "0")
+        plain = model(x)
     assert rel_err(fused, plain) < 2e-6
+    assert rel_err(plain, model(x)) < 1e-7              # grad mode: layer by layer
+    xn = x.clone()
+    xn[::3, :, ::2, 1::3] = float("nan")
+    with torch.no_grad():
+        plain_n = model(xn)
+        monkeypatch.setenv("DPK_DGC_FUSE", "1")
+        fused_n = model(xn)
+    assert rel_err(fused_n, plain_n) < 2e-6
