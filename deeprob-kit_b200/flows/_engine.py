@@ -273,10 +273,12 @@ def linear(x, weight, bias, relu, cache=None):
 
 
 def _mlp_plan(network, x):
-    """[(Linear, relu_follows)] when `network` is a Linear/ReLU stack the tcgen05 GEMM can evaluate for this call
-    (inference on a large fp32 CUDA batch), else None."""
+    """[(Linear, fused_relu, activation_module_or_None)] when `network` is a stack of nn.Linear / MaskedLinear layers
+    with activations that the tcgen05 GEMM can evaluate for this call (inference on a large fp32 CUDA batch), else
+    None.  A ReLU is fused into the GEMM epilogue; any other activation module runs as its own elementwise op."""
     import os
     from torch import nn
+    from ..torch.utils import MaskedLinear
     if (torch.is_grad_enabled() or not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32
             or x.shape[0] < MLP_MIN_BATCH or os.environ.get("DPK_LINEAR_MMA", "1") == "0"):
         return None
@@ -285,12 +287,23 @@ def _mlp_plan(network, x):
     i = 0
     while i < len(mods):
         m = mods[i]
-        if type(m) is not nn.Linear or m.in_features % 4 or m.weight.dtype != torch.float32 or not m.weight.is_contiguous():
+        if (type(m) not in (nn.Linear, MaskedLinear) or m.in_features % 4 or m.weight.dtype != torch.float32
+                or not m.weight.is_contiguous()):
             return None
-        relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
-        plan.append((m, relu))
-        i += 2 if relu else 1
+        act = mods[i + 1] if i + 1 < len(mods) and not isinstance(mods[i + 1], nn.Linear) else None
+        relu = isinstance(act, nn.ReLU)
+        plan.append((m, relu, None if relu else act))
+        i += 1 if act is None else 2
     return plan or None
+
+
+def _layer_weight(m, cache):
+    """Effective weight of a conditioner layer: MaskedLinear multiplies by its fixed 0/1 mask
+    (deeprob/torch/utils.py:73-96); cached until the parameter changes."""
+    mask = getattr(m, "mask", None)
+    if mask is None:
+        return m.weight
+    return _derived(cache, "made_w", (m.weight, mask), lambda: mask * m.weight.detach())
 
 
 def _derived(cache, name, sources, make):
@@ -316,12 +329,15 @@ def mlp(network, x, in_mask=None):
     plan = _mlp_plan(network, x)
     if plan is None:
         return network(x if in_mask is None else in_mask * x)
-    for li, (m, relu) in enumerate(plan):
+    for li, (m, relu, act) in enumerate(plan):
         cache = m.__dict__.setdefault("_dpk_linear_cache", {})
-        weight = m.weight
+        weight = _layer_weight(m, cache)
         if li == 0 and in_mask is not None:
-            weight = _derived(cache, "masked_w", (m.weight, in_mask), lambda: m.weight.detach() * in_mask.reshape(1, -1))
+            src = weight
+            weight = _derived(cache, "masked_w", (src, in_mask), lambda: src.detach() * in_mask.reshape(1, -1))
         x = linear(x, weight, m.bias, relu, cache)
+        if act is not None:
+            x = act(x)
     return x
 
 
@@ -374,6 +390,8 @@ def coupling1d_infer(layer, x, direction, bn=None):
     live_in, live_out, rows = cache["live_in"], cache["live_out"], cache["rows"]
     if live_out.numel() == 0:
         return None
+    if any(type(m) is not torch.nn.Linear or act is not None for m, _, act in plan):
+        return None
     first, last = plan[0][0], plan[-1][0]
     # first layer: live input columns when the mask is 0/1 and their count keeps 16-byte rows, else the fold.  The
     # previous coupling of the chain leaves exactly these columns next to its output (live_out of the C entry)
@@ -395,7 +413,7 @@ def coupling1d_infer(layer, x, direction, bn=None):
         w0 = _derived(cache, "w_first", (first.weight, layer.mask),
                       lambda: first.weight.detach() * layer.mask.reshape(1, -1))
     h = linear(h, w0, first.bias, plan[0][1], first.__dict__.setdefault("_dpk_linear_cache", {}))
-    for m, relu in plan[1:-1]:
+    for m, relu, _ in plan[1:-1]:
         h = linear(h, m.weight, m.bias, relu, m.__dict__.setdefault("_dpk_linear_cache", {}))
     w_l = _derived(cache, "w_last", (last.weight,), lambda: last.weight.detach().index_select(0, rows))
     b_l = None

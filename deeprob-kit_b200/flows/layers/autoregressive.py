@@ -1,5 +1,5 @@
 """Masked autoregressive layer (interface of deeprob/flows/layers/autoregressive.py:13-181): MADE conditioner
-(library GEMMs over masked weights) + the fused affine/log-det kernel of csrc/flows.cu in the density direction;
+(tcgen05 GEMMs over the cached masked weights in inference, library GEMMs with gradients) + the fused affine/log-det kernel of csrc/flows.cu in the density direction;
 the sampling direction is the reference's D-step sequential loop."""
 from typing import List, Optional, Tuple
 
@@ -40,7 +40,8 @@ class AutoregressiveLayer(Bijector):
         self.network = nn.Sequential(*layers)
 
     def apply_backward(self, x):
-        z = self.network(x)
+        # inference on a large batch: the MADE layers (mask * weight cached) run on the tcgen05 GEMM
+        z = _engine.mlp(self.network, x)
         return _engine.coupling(x, z, self.scale_act.weight, None, self.in_features, 0, True, 0, 1)
 
     def _conditioner(self, x):

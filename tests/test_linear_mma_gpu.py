@@ -158,3 +158,42 @@ def test_compact_coupling_entry_matches_plain_layout():
         assert float((out - (ref * pa + pc)).abs().max()) < 1e-5
         assert torch.equal(side, out[:, live])
         assert float((ldj - (ref_ldj + 0.25)).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("activation", ["relu", "tanh"])
+def test_maf_through_the_tensor_core_made(monkeypatch, activation):
+    """MADE conditioner (MaskedLinear = mask * weight, deeprob/torch/utils.py:73-96) on the tcgen05 GEMM in inference
+    against the stock modules; in-place parameter updates are picked up by the cached masked weights."""
+    from deeprob_kit_b200.flows.models import MAF
+    torch.manual_seed(5)
+    model = MAF(64, n_flows=3, depth=2, units=128, batch_norm=True, activation=activation).to(DEV).eval()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    x = torch.randn(2500, 64, device=DEV)
+    for _ in range(2):
+        with torch.no_grad():
+            monkeypatch.setenv("DPK_LINEAR_MMA", "1")
+            ll1 = model(x)
+            monkeypatch.setenv("DPK_LINEAR_MMA", "0")
+            ll0 = model(x)
+        assert rel_err(ll1, ll0) < 1e-5
+        assert rel_err(ll0, model(x)) < 1e-6            # grad mode: stock modules
+        with torch.no_grad():
+            for p in model.parameters():
+                p.mul_(1.03)
+
+
+def test_chained_side_output_is_dropped_after_an_in_place_write():
+    """The compact live-column copy a coupling leaves for the next one is tied to the tensor version: writing to the
+    output in place invalidates it (the next layer gathers again)."""
+    model = _perturbed_nvp(64, False, True, seed=9)
+    x = torch.rand(2500, 64, device=DEV)
+    c0, c1 = model.layers[0], model.layers[1]
+    with torch.no_grad():
+        h, _ = c0.apply_backward(x)
+        assert getattr(h, "_dpk_live", None) is not None
+        ref, _ = c1.apply_backward(h.clone().mul_(2.0))
+        h.mul_(2.0)
+        out, _ = c1.apply_backward(h)
+    assert torch.equal(out, ref)
