@@ -426,8 +426,11 @@ __device__ __forceinline__ float lg2_fast(float v) {
 // taps of every input channel are gathered straight from the product layer's input (lanes = consecutive pixels:
 // row-wise coalesced; the 2x2 neighbourhoods overlap between lanes and rows, so most taps hit L1/L2), the IC
 // product values of NB samples stay in registers for the max pass, the mixture pass and the exact fallback.
+// WG = true (32 channels): the weight block of a tile would need 128 KB of shared memory (one CTA per SM), so the
+// weights are read through L1 instead (each thread re-reads its own column for every sample group: they stay
+// cached) and the CTA may be 64 threads wide for layers of at most 64 pixels.
 template <int IC> struct PsNB { static constexpr int value = IC <= 8 ? 4 : 2; };   // samples a thread carries at once
-template <int IC, int OC>
+template <int IC, int OC, bool WG = false>
 __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wsoft,
                                                               const float* __restrict__ wlog, float* __restrict__ out,
                                                               int64_t B, int O, ProdDesc d, int64_t per_slice) {
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
   constexpr int kPsNB = PsNB<IC>::value;
   const int lane_px = threadIdx.x;
   const int HW = d.OH * d.OW, IHW = d.H * d.W;
-  const int hw = blockIdx.x * 128 + lane_px;
+  const int hw = blockIdx.x * blockDim.x + lane_px;
   const bool live = hw < HW;
   const int oh = live ? hw / d.OW : 0, ow = live ? hw - (hw / d.OW) * d.OW : 0;
   int off[4];
@@ -449,13 +452,16 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
   }
   const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
   for (int o0 = 0; o0 < O; o0 += OC) {
-    __syncthreads();
-    for (int i = 0; i < IC; ++i)
+    if constexpr (!WG) {
+      __syncthreads();
+      for (int i = 0; i < IC; ++i)
 #pragma unroll
-      for (int o = 0; o < OC; ++o)
-        wsm[(i * OC + o) * 128 + lane_px] = (live && o0 + o < O) ? __ldg(wsoft + ((size_t)(o0 + o) * IC + i) * HW + hw) : 0.f;
-    __syncthreads();
+        for (int o = 0; o < OC; ++o)
+          wsm[(i * OC + o) * 128 + lane_px] = (live && o0 + o < O) ? __ldg(wsoft + ((size_t)(o0 + o) * IC + i) * HW + hw) : 0.f;
+      __syncthreads();
+    }
     if (!live) continue;
+    const float* __restrict__ wcol = wsoft + (size_t)o0 * IC * HW + hw;   // WG: this thread's weight column
     // 32-bit element offsets against CTA-uniform slice bases (the host keeps a slice below 2^31 elements): one
     // integer add per load instead of a 64-bit address chain -- the kernel is instruction bound, not HBM bound
     const float* __restrict__ xs = x + (size_t)b0 * IC * IHW;
@@ -505,7 +511,10 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
       for (int i = 0; i < IC; ++i) {
         float w[OC];
 #pragma unroll
-        for (int o = 0; o < OC; ++o) w[o] = wsm[(i * OC + o) * 128 + lane_px];
+        for (int o = 0; o < OC; ++o) {
+          if constexpr (WG) w[o] = (o0 + o < O) ? __ldg(wcol + (unsigned)((o * IC + i) * HW)) : 0.f;
+          else w[o] = wsm[(i * OC + o) * 128 + lane_px];
+        }
 #pragma unroll
         for (int s = 0; s < kPsNB; ++s) {
           const float e = __expf(pv[s][i] - m[s]);
@@ -924,8 +933,8 @@ extern "C" int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const f
   if (!x || !weight || !out || !scratch) return set_error(DPK_E_ARG, "dgc_prodsum: null pointer");
   const ProdDesc d = to_prod(desc);
   const int I = d.OC, hw = d.OH * d.OW;
-  if (!d.depthwise || d.C != d.OC || !(I == 2 || I == 4 || I == 8 || I == 16) || d.sh <= 0 || d.sw <= 0)
-    return set_error(DPK_E_ARG, "dgc_prodsum: only depthwise products with 2, 4, 8 or 16 channels are fused");
+  if (!d.depthwise || d.C != d.OC || !(I == 2 || I == 4 || I == 8 || I == 16 || I == 32) || d.sh <= 0 || d.sw <= 0)
+    return set_error(DPK_E_ARG, "dgc_prodsum: only depthwise products with 2, 4, 8, 16 or 32 channels are fused");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t nw = (size_t)out_channels * I * hw;
   float* wsoft = scratch;
@@ -933,9 +942,11 @@ extern "C" int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const f
   ProfScope prof(CAT_DGC, st, 2);
   dgc_sum_prep_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(weight, wsoft, wlog, out_channels, I, hw);
   DPK_LAUNCH_CHECK("dgc_sum_prep_kernel");
-  const int64_t bx = ceil_div(hw, 128);
+  const bool wg = I == 32;                               // weights through L1 instead of shared memory
+  const int threads = (wg && hw <= 64) ? 64 : 128;
+  const int64_t bx = ceil_div(hw, threads);
   const int OC = out_channels <= 2 ? 2 : (out_channels <= 4 ? 4 : 8);
-  const size_t smem = (size_t)I * OC * 128 * sizeof(float);
+  const size_t smem = wg ? 0 : (size_t)I * OC * 128 * sizeof(float);
   const int64_t per = round_up(ceil_div(batch, std::min<int64_t>(std::max<int64_t>(1, ceil_div((int64_t)env_int_dgc("DPK_DGC_CTAS_PER_SM", 8) * sm_count(), bx)),
                                                                    std::max<int64_t>(1, batch / 64))), 4);
   // the kernel addresses a slice with 32-bit element offsets
@@ -946,7 +957,7 @@ extern "C" int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const f
   {                                                                                                                 \
     auto kern = dgc_prodsum_fwd_kernel<ic_, oc_>;                                                                   \
     if (smem > 48 * 1024) DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 128, smem, st>>>(x, wsoft, wlog, out, batch, out_channels, d, per);                                \
+    kern<<<grid, threads, smem, st>>>(x, wsoft, wlog, out, batch, out_channels, d, per);                            \
   }
 #define DPK_PS_IC(ic_)                                    \
   switch (OC) {                                           \
@@ -958,7 +969,11 @@ extern "C" int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const f
     case 2: DPK_PS_IC(2) break;
     case 4: DPK_PS_IC(4) break;
     case 8: DPK_PS_IC(8) break;
-    default: DPK_PS_IC(16) break;
+    case 16: DPK_PS_IC(16) break;
+    default: {
+      auto kern = dgc_prodsum_fwd_kernel<32, 8, true>;
+      kern<<<grid, threads, 0, st>>>(x, wsoft, wlog, out, batch, out_channels, d, per);
+    } break;
   }
 #undef DPK_PS_IC
 #undef DPK_PS

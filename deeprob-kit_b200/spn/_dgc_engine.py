@@ -172,6 +172,8 @@ def product_mixture(x, desc, weight):
 
 def can_fuse_product_mixture(prod_layer, sum_layer) -> bool:
     d = prod_layer._desc
-    return (bool(d.depthwise) and d.channels == d.out_channels and d.channels in (2, 4, 8, 16)
-            and tuple(sum_layer.weight.shape[1:]) == (d.out_channels, d.out_height, d.out_width)
-            and d.channels * min(8, max(2, sum_layer.weight.shape[0])) * 512 <= 96 * 1024)
+    ok = (bool(d.depthwise) and d.channels == d.out_channels and d.channels in (2, 4, 8, 16, 32)
+          and tuple(sum_layer.weight.shape[1:]) == (d.out_channels, d.out_height, d.out_width))
+    if d.channels == 32:      # weights through L1: output chunks of 8, no shared-memory limit
+        return ok
+    return ok and d.channels * min(8, max(2, sum_layer.weight.shape[0])) * 512 <= 96 * 1024
