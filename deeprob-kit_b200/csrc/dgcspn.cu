@@ -503,10 +503,11 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
         m[s] = (fabsf(mm) <= FLT_MAX) ? mm : 0.f;   // all -inf / non-finite: the exact path sorts it out
       }
       float acc[kPsNB][OC];
+      float2 acc2[kPsNB][OC / 2];
 #pragma unroll
       for (int s = 0; s < kPsNB; ++s)
 #pragma unroll
-        for (int o = 0; o < OC; ++o) acc[s][o] = 0.f;
+        for (int h = 0; h < OC / 2; ++h) acc2[s][h] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < IC; ++i) {
         float w[OC];
@@ -518,10 +519,16 @@ __global__ void __launch_bounds__(128, 3) dgc_prodsum_fwd_kernel(const float* __
 #pragma unroll
         for (int s = 0; s < kPsNB; ++s) {
           const float e = __expf(pv[s][i] - m[s]);
+          const float2 e2 = make_float2(e, e);
 #pragma unroll
-          for (int o = 0; o < OC; ++o) acc[s][o] = fmaf(w[o], e, acc[s][o]);
+          for (int h = 0; h < OC / 2; ++h)          // packed FFMA2: two outputs per instruction
+            acc2[s][h] = __ffma2_rn(make_float2(w[2 * h], w[2 * h + 1]), e2, acc2[s][h]);
         }
       }
+#pragma unroll
+      for (int s = 0; s < kPsNB; ++s)
+#pragma unroll
+        for (int h = 0; h < OC / 2; ++h) { acc[s][2 * h] = acc2[s][h].x; acc[s][2 * h + 1] = acc2[s][h].y; }
       // common case first, without a branch per output; samples with an out-of-range sum are redone exactly.
       // Range check of all sums at once: the minimum catches tiny / negative values, the total catches inf and NaN.
       float amin = FLT_MAX, atot = 0.f;
