@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_kernel(const Ei
 // Register-resident variant for the common sizes (Kin, OC in {2,4,8,10,16}, one output chunk): a thread keeps the
 // right-hand exps and the dL/dr accumulators of its ST samples in registers (j loop fully unrolled), the partition's
 // whole weight block sits in shared memory; only what phase B needs (q, el, er) goes through shared memory.
-template <int OC, int KIN, int ST>
+template <int OC, int KIN, int ST, bool PB2 = false>
 __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_reg_kernel(const EinsumBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   constexpr int NS = kBwdThreads * ST;
@@ -301,8 +301,69 @@ __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_reg_kernel(cons
       for (int k = 0; k < KIN; ++k) gr_out[(size_t)k * a.Bp + b] = gr[s][k] * err[s][k];
     }
   }
-  // ---- phase B: posterior counts M[ij][o] += q_o el_i er_j (lanes = product index ij, warps split the samples) ----
-  if (a.wstat) {
+  // ---- phase B: posterior counts M[ij][o] += q_o el_i er_j ----
+  if constexpr (PB2) {
+    // Register tile: a lane owns one left index i and all (j, o) -- KIN*OC accumulators -- and every KIN lanes
+    // take a different sample, so a step of the warp covers 32/KIN samples with {1 el, KIN er, OC q} shared-memory
+    // loads against KIN*OC/2 packed FFMA2 (lanes = products needed 11 loads per 44 FMA and left the kernel
+    // waiting on the shared-memory queue).  The sample slices are summed with shuffles, the four warps through
+    // shared memory, so a CTA issues K2*OC atomics instead of 4*K2*OC.
+    if (a.wstat) {   // CTA-uniform
+      constexpr int NSL = 32 / KIN, OH = OC / 2;
+      static_assert(OC % 2 == 0 && 4 * K2 * OC <= NS * (QS + KS), "partials must fit the q/el staging area");
+      const int li = lane % KIN, sl = lane / KIN;
+      const bool act = lane < NSL * KIN;
+      float2 m2[KIN][OH];
+#pragma unroll
+      for (int j = 0; j < KIN; ++j)
+#pragma unroll
+        for (int h = 0; h < OH; ++h) m2[j][h] = make_float2(0.f, 0.f);
+      const int s_begin = warp * (NS / 4), s_end = s_begin + NS / 4;
+      if (act) {
+        for (int srow = s_begin + sl; srow < s_end; srow += NSL) {
+          float qv[QS];
+          load_row_smem<QS>(q_sm + (size_t)srow * QS, qv);
+          const float e_l = el[srow * KS + li];
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) {
+            const float pe = e_l * er[srow * KS + j];
+            const float2 pe2 = make_float2(pe, pe);
+#pragma unroll
+            for (int h = 0; h < OH; ++h) m2[j][h] = __ffma2_rn(make_float2(qv[2 * h], qv[2 * h + 1]), pe2, m2[j][h]);
+          }
+        }
+      }
+      // slices -> lane li (sl == 0)
+#pragma unroll
+      for (int j = 0; j < KIN; ++j)
+#pragma unroll
+        for (int h = 0; h < OH; ++h) {
+          float vx = m2[j][h].x, vy = m2[j][h].y;
+#pragma unroll
+          for (int dd = 1; dd < NSL; ++dd) {
+            const float ox = __shfl_sync(0xffffffffu, m2[j][h].x, (lane + dd * KIN) & 31);
+            const float oy = __shfl_sync(0xffffffffu, m2[j][h].y, (lane + dd * KIN) & 31);
+            if (lane + dd * KIN < NSL * KIN) { vx += ox; vy += oy; }
+          }
+          m2[j][h] = make_float2(vx, vy);
+        }
+      __syncthreads();                      // every warp is done with q / el / er: reuse them for the partials
+      float* part = q_sm + (size_t)warp * (K2 * OC);
+      if (lane < KIN) {
+#pragma unroll
+        for (int j = 0; j < KIN; ++j)
+#pragma unroll
+          for (int h = 0; h < OH; ++h)
+            *reinterpret_cast<float2*>(part + (li * KIN + j) * OC + 2 * h) = m2[j][h];
+      }
+      __syncthreads();
+      float* __restrict__ ws = a.wstat + (size_t)p * K2 * OC;
+      for (int t = tid; t < K2 * OC; t += kBwdThreads) {
+        const float v = (q_sm[t] + q_sm[K2 * OC + t]) + (q_sm[2 * K2 * OC + t] + q_sm[3 * K2 * OC + t]);
+        if (v != 0.f) atomicAdd(ws + t, v);
+      }
+    }
+  } else if (a.wstat) {   // lanes = product index ij, warps split the samples
     float* __restrict__ ws = a.wstat + (size_t)p * K2 * OC;
     const int s_begin = warp * (NS / 4), s_end = s_begin + NS / 4;
     for (int blk = 0; blk < K2; blk += 128) {
@@ -623,7 +684,12 @@ static int launch_einsum_bwd_t(const EinsumBwdArgs& a, dim3 grid, size_t smem, c
 template <int OC, int KIN>
 static int launch_einsum_bwd_reg_t(const EinsumBwdArgs& a, cudaStream_t st) {
   constexpr int ST = 2, QS = (OC + 3) / 4 * 4, KS = KIN | 1;
+  // register-tiled posterior counts while the KIN*OC accumulators fit (K, O <= 10); DPK_BWD_PHASEB=0: lanes = products
+  constexpr bool kTile = KIN * OC <= 100 && OC % 2 == 0 && 4 * KIN * KIN * OC <= kBwdThreads * ST * (QS + KS);
   auto kern = ratspn_einsum_bwd_reg_kernel<OC, KIN, ST>;
+  if constexpr (kTile) {
+    if (env_int("DPK_BWD_PHASEB", 1) != 0) kern = ratspn_einsum_bwd_reg_kernel<OC, KIN, ST, true>;
+  }
   const size_t smem = ((size_t)kBwdThreads * ST * (QS + 2 * KS) + (size_t)KIN * KIN * OC) * 4;
   if (smem > 48 * 1024)
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
