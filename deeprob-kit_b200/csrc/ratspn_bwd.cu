@@ -274,9 +274,12 @@ __global__ void __launch_bounds__(kBwdThreads) ratspn_einsum_bwd_reg_kernel(cons
       load_row_smem<OC>(wrow + j * OC, w);
 #pragma unroll
       for (int s = 0; s < ST; ++s) {
-        float T = 0.f;
+        // T = sum_o q_o w_o over output pairs with packed FFMA2 (OC is even), the two halves added at the end
+        float2 T2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int o = 0; o < OC; ++o) T = fmaf(q[s][o], w[o], T);
+        for (int h = 0; h < OC / 2; ++h)
+          T2 = __ffma2_rn(make_float2(q[s][2 * h], q[s][2 * h + 1]), make_float2(w[2 * h], w[2 * h + 1]), T2);
+        const float T = T2.x + T2.y;
         si[s] = fmaf(err[s][j], T, si[s]);
         // el_i as a runtime-indexed register would spill: take it from shared memory (conflict-free, KS odd)
         gr[s][j] = fmaf(el[(tid + s * kBwdThreads) * KS + i], T, gr[s][j]);

@@ -3,6 +3,8 @@
   config 3b DgcSpn((1,28,28), n_batch=16, sum_channels=32, depthwise=True, n_pooling=2)  (MNIST example setting)
   config 4  RealNVP1d(3072, n_flows=8, depth=2, units=512), batch 16384
   config 1  BernoulliRatSpn(15, 3, 4, 4, 2) on all 2^15 states
+The CPU oracle (oracle/) is imported here only as the timed CPU comparator, the same role it has in bench.py's
+cpu_baseline leg; nothing on the measured GPU path touches it.
 Prints one JSON line per config:   python profiles/bench_configs.py [--no-cpu] [--only NAME]"""
 import json
 import os
