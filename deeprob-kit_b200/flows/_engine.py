@@ -400,10 +400,12 @@ def coupling1d_infer(layer, x, direction, bn=None):
         h = None
         hint = getattr(x, "_dpk_live", None)
         if hint is not None and hint[2] == x._version and hint[1].shape[0] == batch:
-            same = cache.setdefault("hint_ok", {})
-            if hint[0].data_ptr() not in same:
-                same[hint[0].data_ptr()] = hint[0].shape == live_in.shape and bool(torch.equal(hint[0], live_in))
-            if same[hint[0].data_ptr()]:
+            same = cache.setdefault("hint_ok", {})      # index tensor (kept alive: its address stays unique) -> verdict
+            known = same.get(hint[0].data_ptr())
+            if known is None or known[0] is not hint[0]:
+                known = (hint[0], hint[0].shape == live_in.shape and bool(torch.equal(hint[0], live_in)))
+                same[hint[0].data_ptr()] = known
+            if known[1]:
                 h = hint[1]
         if h is None:
             h = x.index_select(1, live_in)
