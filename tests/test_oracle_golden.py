@@ -62,3 +62,19 @@ def test_oracle_against_live_reference():
     x[::3, ::4] = float("nan")
     assert rel_err(orc.log_prob(x), ref(x)) < 1e-6
     del cfg
+
+
+def test_oracle_is_a_normalised_distribution_over_all_binary_states():
+    """The reference's own known-answer property for this path (tests/test_ratspn.py:46-48): a Bernoulli RAT-SPN
+    over 15 binary variables sums to one over the 2^15 complete states; with marginalised variables (NaN,
+    tests/utils.py random_marginalize_data) the remaining ones still do."""
+    cfg = pg.RATSPN_CASES["bern15"]
+    orc, _ = oracle_for(cfg)
+    states = ((torch.arange(2 ** 15).unsqueeze(1) >> torch.arange(14, -1, -1)) & 1).float()
+    ll = orc.log_prob(states).double().reshape(-1)
+    assert abs(float(torch.logsumexp(ll, 0))) < 1e-4
+    # marginalise the last 5 variables: 2^10 states of the first 10, each listed once
+    sub = states[:: 2 ** 5].clone()
+    sub[:, 10:] = float("nan")
+    llm = orc.log_prob(sub).double().reshape(-1)
+    assert abs(float(torch.logsumexp(llm, 0))) < 1e-4
