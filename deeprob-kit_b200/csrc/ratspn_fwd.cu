@@ -28,8 +28,7 @@ extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, i
   int rc = make_plan(desc, batch, flags & DPK_F_SAVE_ACTIVATIONS, &p);
   if (rc) return rc;
   if (batch == 0) return DPK_OK;
-  if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0 || !desc->root_weight ||
-      false)
+  if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0 || !desc->root_weight)
     return set_error(DPK_E_ARG, "null pointer argument");
   for (int e = 0; e < p.n_sum; ++e)
     if (!desc->sum_weight[e]) return set_error(DPK_E_ARG, "null sum_weight[%d]", e);

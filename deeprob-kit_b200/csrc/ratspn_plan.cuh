@@ -153,8 +153,11 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
   {
     const int knob = env_int("DPK_LEAF_MMA", -1);
     const size_t mma_smem = (size_t)kMmaStages * 4 * kMmaTileN * kMmaKB * 2 + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+    // R*K columns per feature: below ~24 the level is HBM bound, not FMA bound, and the CUDA-core
+    // kernel -- which reads x exactly once -- beats the GEMM with its extra pass over the operand images
+    const bool wide = p->R * p->K >= env_int("DPK_LEAF_MMA_MIN_RK", 24);
     p->leaf_mma = (p->D % 4 == 0 && knob != 0 &&
-                   (batch >= kMmaMinBatch || knob == 1) && mma_smem <= (size_t)max_dynamic_smem())
+                   ((batch >= kMmaMinBatch && wide) || knob == 1) && mma_smem <= (size_t)max_dynamic_smem())
                       ? 1 : 0;
     p->mma_nS = p->mma_nW = p->mma_kb = 0;
     p->off_wimg = p->off_simg = p->off_cstm = p->off_sq = p->off_mflags = p->off_aimg = 0;

@@ -16,6 +16,26 @@ from .densenet import DenseNetwork
 from .resnet import ResidualNetwork
 
 
+class _Fp32ConvBackward(torch.autograd.Function):
+    """Identity behind a conv conditioner.  Its backward runs before every backward node of the conditioner: it
+    turns cuDNN's TF32 convolutions off and queues the restore for the end of the running backward pass."""
+
+    @staticmethod
+    def forward(ctx, z):
+        return z.view_as(z)
+
+    @staticmethod
+    def backward(ctx, g):
+        prev = torch.backends.cudnn.allow_tf32
+        if prev:
+            torch.backends.cudnn.allow_tf32 = False
+
+            def restore():
+                torch.backends.cudnn.allow_tf32 = True
+            torch.autograd.Variable._execution_engine.queue_callback(restore)
+        return g
+
+
 class CouplingLayer1d(Bijector):
     def __init__(self, in_features: int, depth: int, units: int, affine: bool = True, reverse: bool = False):
         super().__init__(in_features)
@@ -70,10 +90,6 @@ class CouplingLayer2d(Bijector):
         self.affine = affine
         self.channelwise = channelwise
         self.reverse = reverse
-        # cuDNN would otherwise run the fp32 conditioner convolutions (forward AND backward) on TF32 tensor
-        # cores (10-bit mantissa); the 1e-4 parity bar of the log-likelihood needs true fp32.  The backward runs
-        # later inside autograd, so a scoped flag cannot cover it: the process-wide switch is turned off here.
-        torch.backends.cudnn.allow_tf32 = False
         if not channelwise:
             mask, inv_mask = self.build_checkerboard_masks()
             if reverse:
@@ -112,7 +128,17 @@ class CouplingLayer2d(Bijector):
         return mask, 1.0 - mask
 
     def _conditioner(self, x):
-        return self.network(x)
+        # cuDNN would otherwise run the fp32 conditioner convolutions (forward AND backward) on TF32 tensor cores
+        # (10-bit mantissa); the 1e-4 parity bar of the log-likelihood needs true fp32.  The switch is scoped to
+        # this conditioner: off around its forward, and off again from the moment autograd enters its backward
+        # until the end of that backward pass (see _Fp32ConvBackward); the process-wide setting is restored.
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            z = self.network(x)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        return _Fp32ConvBackward.apply(z) if z.requires_grad else z
 
     def _transform(self, x, direction):
         hw = self.in_height * self.in_width

@@ -134,23 +134,36 @@ class _Root(torch.autograd.Function):
         return (gx.reshape(ctx.in_shape) if gx is not None else None), gw
 
 
+def _check_shape(x, expect, what):
+    """The kernels take C/H/W from the parameters / descriptor: a mismatching input would read out of bounds."""
+    if tuple(x.shape[1:]) != tuple(expect):
+        raise ValueError("%s: expected a (B, %s) tensor, got %s" % (what, ", ".join(str(int(e)) for e in expect), tuple(x.shape)))
+
+
 def leaf(x, loc, scale):
     x = _check4d(x, "SpatialGaussianLayer.forward")
+    _check_shape(x, loc.shape[1:], "SpatialGaussianLayer.forward")
+    if tuple(scale.shape) != tuple(loc.shape):
+        raise ValueError("SpatialGaussianLayer.forward: loc %s and scale %s differ in shape" % (tuple(loc.shape), tuple(scale.shape)))
     return _Leaf.apply(x, loc, scale)
 
 
 def product(x, desc):
     x = _check4d(x, "SpatialProductLayer.forward")
+    _check_shape(x, (desc.channels, desc.height, desc.width), "SpatialProductLayer.forward")
     return _Product.apply(x, desc)
 
 
 def mixture(x, weight):
     x = _check4d(x, "SpatialSumLayer.forward")
+    _check_shape(x, weight.shape[1:], "SpatialSumLayer.forward")
     return _Sum.apply(x, weight)
 
 
 def root(x, weight):
     _lib.require_cuda(x, "SpatialRootLayer.forward")
+    if x.dim() < 2 or x[0].numel() != weight.shape[1]:
+        raise ValueError("SpatialRootLayer.forward: expected %d values per sample, got %s" % (weight.shape[1], tuple(x.shape)))
     return _Root.apply(x, weight)
 
 
@@ -159,6 +172,9 @@ def product_mixture(x, desc, weight):
     (dpk_dgc_prodsum_forward): the product output is never materialised.  No autograd node: callers use it only
     when no gradient is needed."""
     x, weight = _check4d(x, "SpatialProductLayer.forward"), _f32c(weight.detach())
+    _check_shape(x, (desc.channels, desc.height, desc.width), "SpatialProductLayer.forward")
+    if tuple(weight.shape[1:]) != (desc.out_channels, desc.out_height, desc.out_width):
+        raise ValueError("SpatialSumLayer.forward: weight %s does not match the product output" % (tuple(weight.shape),))
     b = x.shape[0]
     cout = weight.shape[0]
     out = torch.empty(b, cout, desc.out_height, desc.out_width, dtype=torch.float32, device=x.device)

@@ -88,19 +88,33 @@ def m_step(model, stats: Dict, step_size: float = 0.5) -> None:
         p_new = p_new.clamp(1e-7, 1.0 - 1e-7)
         base.logits.copy_(torch.where(live, torch.log(p_new) - torch.log1p(-p_new), base.logits))
     else:
-        s2 = stats["s2"]
+        s2 = stats.get("s2")
         total = s0 + _EPS32
         mean = s1 / total
-        var = (s2 - 2.0 * mean * s1 + mean * mean * s0) / total
-        std = torch.sqrt(var.clamp_min(0.0)).clamp_min(1e-5)
         base.loc.copy_(torch.where(live, (1.0 - eta) * base.loc + eta * mean, base.loc))
-        base.scale.copy_(torch.where(live, (1.0 - eta) * base.scale + eta * std, base.scale))
+        # A frozen unit scale (the default optimize_scale=False, layers/ratspn.py:198-207) stays frozen: the E-step
+        # then returns no second moment (s2 is None) and only the means are re-estimated.
+        if s2 is not None and base.scale.requires_grad:
+            var = (s2 - 2.0 * mean * s1 + mean * mean * s0) / total
+            std = torch.sqrt(var.clamp_min(0.0)).clamp_min(1e-5)
+            base.scale.copy_(torch.where(live, (1.0 - eta) * base.scale + eta * std, base.scale))
 
 
-def em_step(model, x: torch.Tensor, step_size: float = 0.5, group=None) -> float:
-    """One (optionally batch-sharded) EM step on this rank's shard `x`; returns the global mean log-likelihood."""
+def em_step(model, x: torch.Tensor, step_size: float = 0.5, group=None, timing: Optional[Dict] = None) -> float:
+    """One (optionally batch-sharded) EM step on this rank's shard `x`; returns the global mean log-likelihood.
+    `timing` (optional dict) collects a pair of CUDA events around the all-reduce of every step under
+    "allreduce" and the size of the exchanged vector under "bytes" (bench.py reports them)."""
     stats = model.em_statistics(x)
-    flat = all_reduce_statistics(pack_statistics(stats, x.shape[0]), group)
+    flat = pack_statistics(stats, x.shape[0])
+    if timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flat = all_reduce_statistics(flat, group)
+        e1.record()
+        timing.setdefault("allreduce", []).append((e0, e1))
+        timing["bytes"] = flat.numel() * 4
+    else:
+        flat = all_reduce_statistics(flat, group)
     glob = unpack_statistics(flat, stats)
     m_step(model, glob, step_size)
     return float(glob["ll_sum"] / glob["n"])

@@ -116,3 +116,14 @@ def test_fused_product_sum_matches_layerwise(name, monkeypatch):
         monkeypatch.setenv("DPK_DGC_FUSE", "1")
         fused_n = model(xn)
     assert rel_err(fused_n, plain_n) < 2e-6
+
+
+def test_shape_mismatch_raises_instead_of_reading_out_of_bounds():
+    """the kernels take C/H/W from the parameters; a different input shape must raise like the
+    reference's broadcast / conv shape errors do."""
+    cfg = pg.DGCSPN_CASES[sorted(pg.DGCSPN_CASES)[0]]
+    model = dgc_product_model(cfg, DEV)
+    c, h, w = cfg["in_features"]
+    for shape in ((2, c + 1, h, w), (2, c, h + 1, w), (2, c, h, w - 1)):
+        with pytest.raises(ValueError):
+            model(torch.zeros(*shape, device=DEV))

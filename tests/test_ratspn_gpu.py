@@ -237,3 +237,60 @@ def test_em_steps_increase_likelihood():
     for _ in range(5):
         em.em_step(bern, xb, step_size=0.5)
     assert float(bern(xb).mean()) > l0 + 0.1
+
+
+def test_em_step_with_frozen_unit_scale():
+    """the default GaussianRatSpn (optimize_scale=False) has no second moment (s2 is None) and a frozen
+    scale: the M-step re-estimates the means only, the scale stays 1, the likelihood still rises."""
+    from deeprob_kit_b200.spn import em
+    from deeprob_kit_b200.spn.models import GaussianRatSpn
+    gen = torch.Generator().manual_seed(3)
+    centers = torch.randn(3, 16, generator=gen) * 1.5
+    x = (centers[torch.randint(0, 3, (2048,), generator=gen)] + torch.randn(2048, 16, generator=gen)).to(DEV)
+    torch.manual_seed(0)
+    model = GaussianRatSpn(16, rg_depth=2, rg_repetitions=4, rg_batch=4, rg_sum=3, random_state=42).to(DEV)
+    assert model.base_layer.unit_scale()
+    st = model.em_statistics(x)
+    assert st["s2"] is None
+    l0 = float(model(x).mean())
+    for _ in range(4):
+        em.em_step(model, x, step_size=0.5)
+    assert float(model(x).mean()) > l0 + 1.0
+    assert bool((model.base_layer.scale == 1).all())
+
+
+def test_log_prob_host_result_is_complete_on_return():
+    """the pinned result of log_prob_host can be read as soon as the call returns."""
+    from deeprob_kit_b200.spn.streaming import log_prob_host
+    cfg = pg.RATSPN_CASES["gauss_cls"]
+    model = product_model(cfg, DEV)
+    rng = np.random.RandomState(11)
+    x = torch.from_numpy(rng.standard_normal((5000, cfg["in_features"])).astype(np.float32)).pin_memory()
+    ref = model(x.to(DEV)).cpu()
+    for _ in range(3):
+        out = log_prob_host(model, x, chunk=1024)
+        got = out.clone()                       # read immediately, no synchronize in between
+        assert torch.equal(got, ref)
+        out.fill_(float("nan"))                 # next round must overwrite every element again
+    oh = torch.full((5000, cfg["out_classes"]), float("nan")).pin_memory()
+    assert torch.equal(log_prob_host(model, x, chunk=777, out_host=oh).clone(), ref)
+    empty = log_prob_host(model, x[:0])
+    assert empty.shape == (0, cfg["out_classes"])
+
+
+def test_cache_invalidation_and_copies():
+    """ADVICE r1: a write through .data is invisible to the version-keyed table cache until invalidate_caches();
+    deepcopy / pickling carry no workspaces."""
+    import copy
+    cfg = pg.RATSPN_CASES["gauss_d1"]
+    model = product_model(cfg, DEV)
+    x, _ = pg.ratspn_inputs(cfg)
+    xd = x.to(DEV)
+    a = model(xd).clone()
+    model(xd)                                   # second call: tables cached
+    model.base_layer.loc.data.add_(0.25)
+    model.invalidate_caches()
+    b = model(xd)
+    assert not torch.allclose(a, b)
+    twin = copy.deepcopy(model)
+    assert twin._ws_cache == {} and torch.equal(twin(xd), b)
