@@ -97,3 +97,33 @@ extern "C" int dpk_profile_read(double* ms, int64_t* launches, int32_t ncat) {
   }
   return rc;
 }
+
+// ---- TMA tensor maps ---------------------------------------------------------------------------------
+#include <cudaTypedefs.h>
+
+#include "tc_common.cuh"
+namespace dpk {
+namespace tc {
+int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                           uint32_t box_rows, uint32_t box_cols) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+      return set_error(DPK_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {row_stride_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return set_error(DPK_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  return DPK_OK;
+}
+}  // namespace tc
+}  // namespace dpk

@@ -36,10 +36,12 @@ extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, i
   float* ws = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!(flags & DPK_F_TABLES_VALID)) {
-    ProfScope prof(CAT_PREP, st, 3 + 2 * p.n_sum + (p.leaf_mma ? 2 : 0));
+    ProfScope prof(CAT_PREP, st, 3 + 2 * p.n_sum + (p.leaf_mma ? 2 : 0) + (p.tree_mma ? p.depth : 0));
     if ((rc = ratspn_run_prep_leaf(desc, p, ws, st))) return rc;
     if ((rc = ratspn_run_prep_weights(desc, p, ws, st))) return rc;
+    if (p.tree_mma && (rc = ratspn_run_prep_tree(p, ws, st))) return rc;
   }
   if ((rc = ratspn_run_leaf(desc, p, x, ws, st))) return rc;
+  if (p.tree_mma) return ratspn_run_tree(p, ws, out, st);
   return ratspn_run_upper(p, ws, out, st);
 }

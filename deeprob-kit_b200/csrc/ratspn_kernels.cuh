@@ -22,6 +22,9 @@ size_t ratspn_einsum_mma_image_floats(int P, int Kin, int O);
 int ratspn_run_prep_einsum_mma(const float* wsoft, int P, int O, int Kin, int OC, float* wimg, cudaStream_t st);
 int ratspn_run_einsum_mma(const float* in, const float* wimg, const float* wsoft, const float* wlog, float* out, int64_t Bp, int P, int Kin,
                           int O, int OC, int cat, cudaStream_t st);
+// all product + sum levels and the root fused, mixtures on tcgen05 (inference)      [ratspn_tree_mma.cu]
+int ratspn_run_prep_tree(const RatPlan& p, float* ws, cudaStream_t st);
+int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st);
 // x -> act[0]                                                      [ratspn_leaf.cu]
 int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, float* ws, cudaStream_t st);
 // act[0] -> ... -> out (B, C)                                      [ratspn_einsum.cu]

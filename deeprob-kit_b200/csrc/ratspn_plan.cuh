@@ -19,6 +19,9 @@ namespace dpk {
 //   root          rsoft/rlog [R][nCc][Kin^2][CC]
 //   activations   act[l] [G_l][ch_l][Bp]  (sample-minor so that lanes = samples coalesce)
 //   grad of act   gact[l] same shapes (only with DPK_F_SAVE_ACTIVATIONS)
+constexpr int kTreeMaxD = 4;   // deepest region graph the fused tree kernel walks (ratspn_tree_mma.cu)
+bool ratspn_tree_instantiated(int KL, int O);
+
 struct RatPlan {
   int kind, D, depth, R, K, O, C, dim, G0;
   int fwd_kind;  // table/kernel flavour: DPK_LEAF_GAUSSIAN, DPK_LEAF_BERNOULLI or kLeafGaussUnit (scale == 1 everywhere)
@@ -47,6 +50,10 @@ struct RatPlan {
   size_t off_wmma[DPK_MAX_LEVELS];     // its weight images
   size_t off_rsoft, off_rlog, r_floats;
   size_t off_rtmp;  // [R][C][Bp] per-partition partials of the root
+  // fused upper levels on the tensor cores (ratspn_tree_mma.cu): 0 = not used for this call
+  int tree_mma, tree_G, tree_tcols;
+  size_t off_timg;                       // [R][tree_rep_bytes] tf32 hi/lo weight images of every partition of a repetition
+  uint32_t tree_rep_bytes, tree_off[kTreeMaxD + 1], tree_npad[kTreeMaxD + 1];
   size_t off_act[DPK_MAX_LEVELS], off_gact[DPK_MAX_LEVELS];
   // backward scratch (only with DPK_F_SAVE_ACTIVATIONS): posterior-count accumulators in the chunked
   // weight layouts and leaf moment accumulators in the parameter layout (G0,K,dim)
@@ -194,6 +201,33 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     p->off_rlog = take(p->r_floats);
   }
   p->off_rtmp = take((size_t)p->R * p->C * p->Bp);
+  // Inference only: all product + sum levels and the root as one tensor-core kernel (DPK_TREE_MMA=0 disables it,
+  // =1 forces it for any batch size).  The backward needs every level's activations, so it keeps the layer-wise path.
+  p->tree_mma = 0; p->tree_G = 0; p->tree_tcols = 0; p->off_timg = 0; p->tree_rep_bytes = 0;
+  {
+    const int knob = env_int("DPK_TREE_MMA", -1);
+    const int Osel = (p->depth == 1) ? p->K : p->O;
+    if (knob != 0 && !(flags & DPK_F_SAVE_ACTIVATIONS) && (batch >= kMmaMinBatch || knob == 1) && p->depth <= kTreeMaxD &&
+        ratspn_tree_instantiated(p->K, Osel)) {
+      uint32_t off = 0, nmax = 0;
+      for (int lvl = 0; lvl < p->depth; ++lvl) {
+        const int Kin = (lvl == 0) ? p->K : p->O;
+        const int Nout = (lvl == p->depth - 1) ? p->C : p->O;
+        const uint32_t npad = (uint32_t)round_up((int64_t)Kin * Nout, 16);
+        p->tree_off[lvl] = off; p->tree_npad[lvl] = npad;
+        off += (uint32_t)(1 << (p->depth - 1 - lvl)) * 2u * npad * 64u;
+        nmax = std::max(nmax, npad);
+      }
+      const int Kr = (p->depth == 1) ? p->K : p->O;
+      const int tcols = nmax <= 128 ? 128 : 256;
+      const int G = 512 / tcols;
+      const size_t smem = 1024 + (((size_t)off + 1023) & ~(size_t)1023) + (size_t)G * (16384 + 2 * p->K * 512) + 128;
+      if (nmax <= 256 && (p->C - 1) * Kr + 16 <= tcols && smem <= (size_t)max_dynamic_smem()) {
+        p->tree_mma = 1; p->tree_G = G; p->tree_tcols = tcols; p->tree_rep_bytes = off;
+        p->off_timg = take((size_t)p->R * off / 4);
+      }
+    }
+  }
   for (int l = 0; l < p->depth; ++l)
     p->off_act[l] = take((size_t)p->act_regions[l] * p->act_ch[l] * p->Bp);
   for (int l = 0; l < p->depth; ++l)

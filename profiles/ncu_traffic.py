@@ -18,7 +18,7 @@ def short_name(full):
     name = m.group(1) if m else full
     targs = (m.group(2) or "") if m else ""
     if name == "ratspn_leaf_mma_kernel":
-        return name + ("<prep>" if re.match(r"<\(bool\)1|<true", targs) else "<main>")
+        return name + ("<prep>" if re.match(r"<\s*(\(bool\))?\s*(1|true)\b", targs) else "<main>")
     return name
 
 
