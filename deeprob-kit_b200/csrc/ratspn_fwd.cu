@@ -1,5 +1,7 @@
 // ratspn_fwd.cu -- C-ABI entry points of the RAT-SPN forward (RatSpn.forward,
 // deeprob/spn/models/ratspn.py:105-122): parameter tables -> leaf level -> product+sum levels -> root.
+#include <algorithm>
+
 #include "ratspn_kernels.cuh"
 
 namespace dpk {
@@ -17,9 +19,11 @@ int ratspn_check_ws(const RatPlan& p, const void* ws, size_t bytes) {
 using namespace dpk;
 
 extern "C" size_t dpk_ratspn_workspace_bytes(const dpk_ratspn_desc* desc, int64_t batch, uint32_t flags) {
-  RatPlan p;
+  // one buffer serves dpk_ratspn_forward and the stand-alone leaf layer (dpk_ratspn_leaf_forward), whose plans differ
+  RatPlan p, q;
   if (make_plan(desc, batch, flags & DPK_F_SAVE_ACTIVATIONS, &p)) return 0;
-  return p.total_floats * sizeof(float);
+  if (make_plan(desc, batch, (flags & DPK_F_SAVE_ACTIVATIONS) | kPlanLeafOnly, &q)) return 0;
+  return std::max(p.total_floats, q.total_floats) * sizeof(float);
 }
 
 extern "C" int dpk_ratspn_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,

@@ -503,7 +503,7 @@ using namespace dpk;
 extern "C" int dpk_ratspn_leaf_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,
                                        void* workspace, size_t workspace_bytes, void* stream) {
   RatPlan p;
-  int rc = make_plan(desc, batch, 0, &p);
+  int rc = make_plan(desc, batch, kPlanLeafOnly, &p);
   if (rc) return rc;
   if (batch == 0) return DPK_OK;
   if (!x || !out || !desc->mask || !desc->region_len || !desc->leaf_p0)

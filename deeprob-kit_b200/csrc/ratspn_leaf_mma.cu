@@ -73,6 +73,7 @@ struct LeafMmaArgs {
   int gen;                    // general Gaussian: x^2 images go to the global scratch too (K blocks KBn/2 .. KBn-1)
   int64_t lda;                // row stride of x (elements); columns >= D read as 0
   int nC, kchunk;             // split-K: nC chunks of kchunk K blocks (nC == 1: the whole K range per unit)
+  float* sqsum;               // CONV launch of a unit-scale Gaussian: [Bp] -1/2 sum_f x_f^2 per sample (else NULL)
   float ascale, oscale;       // PREP multiplies the A operand by ascale; linear == 2 multiplies the result by oscale
   int linear, relu;           // linear == 2: out (B, Ntot) += result (atomic, split-K partial sums); linear != 0: generic layer, out (B, Ntot) row-major = act(x W^T + bias), cstm = bias
   unsigned long long* stats;  // debug (DPK_MMA_STATS=1): cycles per role spent waiting, else NULL
@@ -164,7 +165,14 @@ constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units
 
 // GEN (PREP launch of a general Gaussian only) is a template parameter: as a run-time branch in the conversion loop
 // it cost the unit-scale path 19 % (0.135 -> 0.160 ms) through the register allocation of that loop.
-template <bool PREP, bool GEN = false>
+// CONV (main launch only): no PREP launch and no operand images in global memory -- the feeder warps read the fp32
+// inputs themselves (the same 4 bytes per element as the hi/lo fp16 images; every M tile is re-read from L2 by its
+// N-tile units), split them and store the hi/lo images straight into the shared-memory stages.  The first N tile of
+// an M tile also checks the input range and accumulates -1/2 sum_f x_f^2 per sample: for a unit-scale Gaussian the
+// quadratic term of EVERY leaf of a repetition adds up to that one number (the leaf regions of a repetition
+// partition the features), so it factors out of all sum nodes and is added once to the final log-likelihood
+// (ratspn_tree_mma.cu) instead of per region here.
+template <bool PREP, bool GEN = false, bool CONV = false>
 __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const LeafMmaArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   const bool tensor = !PREP || a.quad != 0;
 
   if (__ldg(a.wflag) != 0) {  // parameters outside the fp16 range: the exact kernel does everything
-    if (PREP)
+    if (PREP || CONV)
       for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.Bp / 32; i += (int64_t)gridDim.x * blockDim.x)
         a.redo[i] = 1;
     return;
@@ -422,6 +430,89 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
           if (kb + 1 < kbe) {
             convert(kb + 1, bufB);
             if (kb + 3 < kbe) load(kb + 3, bufB);
+          }
+        }
+      } else if constexpr (CONV) {
+        // Branch-free converter: 8 predicated 16-byte loads per K block (rows b0 + 4 i, features 4 c8 .. 4 c8 + 3 of
+        // the block), explicit byte addresses stepped by constants, two precomputed swizzled store offsets (rows
+        // 4 i + rsub differ from row rsub by 256 i bytes, and in the swizzle term only through the parity of i).
+        const int cw = warp - 2;
+        const int c8 = lane & 7, rsub = lane >> 3;
+        const bool first = (j == 0);
+        const bool sqs = first && a.sqsum != nullptr;
+        const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vmask |= (b0 + 4 * i < a.B) ? (1u << i) : 0u;
+        const char* xb = reinterpret_cast<const char*>(a.x) + ((size_t)b0 * a.lda + (size_t)c8 * 4) * 4;
+        const size_t rstride = (size_t)a.lda * 16;     // four rows down, in bytes
+        const uint32_t row0 = cw * 32 + rsub;
+        const uint32_t off_e = sw64_off(row0, c8 >> 1) + (c8 & 1) * 8;
+        const uint32_t off_o = sw64_off(row0 + 4, c8 >> 1) + (c8 & 1) * 8 - 256;
+        float sqacc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sqacc[i] = 0.f;
+        uint32_t umax = 0;                              // running max of |x| as ordered bits (NaN / inf sort above every finite value)
+        auto load = [&](int kb, float4 (&v)[8]) {
+          const bool fok = kb * kMmaKB + c8 * 4 < a.D;
+          const char* p = xb + (size_t)kb * (kMmaKB * 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t pred = (fok && ((vmask >> i) & 1u)) ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                         "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+                         "@p ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                         : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                         : "l"(p + (size_t)i * rstride), "r"(pred));
+          }
+        };
+        auto convert = [&](float4 (&buf)[8]) {
+          wait_empty();
+          unsigned char* A = sm + stage * kStage;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = buf[i];
+            if (first) {
+              umax = max(umax, max(max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu),
+                                   max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
+              if (sqs) sqacc[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, sqacc[i]))));
+            }
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+            lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+            const uint32_t off = ((i & 1) ? off_o : off_e) + (uint32_t)i * 256u;
+            *reinterpret_cast<uint2*>(A + off) = hv;
+            *reinterpret_cast<uint2*>(A + kImg + off) = lv;
+          }
+          publish();
+        };
+        // two register sets, loads two K blocks ahead of their use (no register copies: a copy would wait for the load)
+        float4 bufA[8], bufB[8];
+        load(kb0, bufA);
+        if (kb0 + 1 < kb1) load(kb0 + 1, bufB);
+        for (int kb = kb0; kb < kb1; kb += 2) {
+          convert(bufA);
+          if (kb + 2 < kb1) load(kb + 2, bufA);
+          if (kb + 1 < kb1) {
+            convert(bufB);
+            if (kb + 3 < kb1) load(kb + 3, bufB);
+          }
+        }
+        if (first) {
+          // all 8 rows of a thread lie in one 32-sample group (rows cw*32 .. cw*32 + 31)
+          if (umax > __float_as_uint(a.xlimit)) a.redo[b0 >> 5] = 1;
+          if (sqs) {   // the 8 lanes of a row group hold the 8 four-feature columns of their rows
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v = sqacc[i];
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              if (c8 == 0 && b0 + 4 * i < a.Bp) a.sqsum[b0 + 4 * i] = -0.5f * v;
+            }
           }
         }
       } else {
@@ -862,12 +953,25 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   DPK_CUDA_TRY(cudaMemsetAsync(a.redo, 0, mma_call_flag_ints(p) * 4, st));
   a.xlimit = (a.quad || a.gen) ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
   a.linear = 0; a.relu = 0; a.nC = 1; a.kchunk = a.KBn; a.ascale = 1.f; a.oscale = 1.f; a.lda = a.D;
+  a.sqsum = nullptr;
   const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
   a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.redo + p.Bp / 32 + 4) : nullptr;
   if (want_stats) DPK_CUDA_TRY(cudaMemsetAsync(a.stats, 0, 32 * 8, st));
   const int cap = std::min(sm_count(), env_int("DPK_MMA_GRID", 1 << 30));
   const int grid_prep = std::min(cap, a.nM * std::max(a.nS, 1)), grid_main = std::min(cap, a.nM * a.nW);
   const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+  if (p.leaf_conv) {
+    // one launch: the feeders convert x themselves; the quadratic term of a unit-scale Gaussian leaves as one
+    // number per sample (sqsum) that ratspn_tree_mma.cu adds at the root.  No x^2 image -> only x itself has to stay
+    // inside the fp16 hi/lo range.
+    a.sqsum = a.quad ? ws + p.off_sqsum : nullptr;
+    a.quad = 0;
+    a.xlimit = 30000.f;
+    DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(CAT_LEAF_MMA, st);
+    ratspn_leaf_mma_kernel<false, false, true><<<grid_main, kThreads, smem, st>>>(a);
+    DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<conv>");
+  } else {
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
@@ -884,6 +988,7 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
     ProfScope prof(CAT_LEAF_MMA, st);
     ratspn_leaf_mma_kernel<false><<<grid_main, kThreads, smem, st>>>(a);
     DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main>");
+  }
   }
   if (want_stats) {   // debug only: synchronises
     unsigned long long h[32];
@@ -942,7 +1047,7 @@ int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const 
   a.redo = flg; a.unit_counter = flg + n_redo; a.wflag = wflag;
   // P = posterior * grad_out: 2^14 keeps posteriors in [0, 1] inside the fp16 range and drops the subnormal floor
   a.ascale = 16384.f; a.oscale = 1.f / 16384.f; a.xlimit = 60000.f;
-  a.linear = 2; a.relu = 0; a.stats = nullptr;
+  a.linear = 2; a.relu = 0; a.stats = nullptr; a.sqsum = nullptr;
   a.kchunk = 64; a.nC = (int)ceil_div(KBn, a.kchunk);   // <= 384 accumulations per accumulator: 2e-5 relative
   const int cap = sm_count();
   const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
@@ -1014,7 +1119,7 @@ extern "C" int dpk_linear_forward(const float* x, const float* weight, const flo
   a.wimg = ws + p.off_wimg; a.simg = nullptr; a.aimg = ws + p.off_aimg;
   a.cstm = bias; a.sq = nullptr; a.out = out;
   a.redo = flg; a.unit_counter = flg + p.Bp / 32; a.wflag = flg + p.Bp / 32 + 3;
-  a.xlimit = 60000.f; a.linear = 1; a.relu = relu ? 1 : 0; a.stats = nullptr;
+  a.xlimit = 60000.f; a.linear = 1; a.relu = relu ? 1 : 0; a.stats = nullptr; a.sqsum = nullptr;
   a.nC = 1; a.kchunk = a.KBn; a.ascale = 1.f; a.oscale = 1.f; a.lda = a.D;
   if (!(flags & DPK_F_TABLES_VALID)) {
     ProfScope prof(CAT_PREP, st, 1);

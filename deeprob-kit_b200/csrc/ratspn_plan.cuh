@@ -19,6 +19,7 @@ namespace dpk {
 //   root          rsoft/rlog [R][nCc][Kin^2][CC]
 //   activations   act[l] [G_l][ch_l][Bp]  (sample-minor so that lanes = samples coalesce)
 //   grad of act   gact[l] same shapes (only with DPK_F_SAVE_ACTIVATIONS)
+constexpr uint32_t kPlanLeafOnly = 1u << 30;   // internal make_plan flag: stand-alone leaf layer (act[0] must be the true leaf LL)
 constexpr int kTreeMaxD = 4;   // deepest region graph the fused tree kernel walks (ratspn_tree_mma.cu)
 bool ratspn_tree_instantiated(int KL, int O);
 
@@ -41,6 +42,8 @@ struct RatPlan {
   size_t leaf_smem;       // dynamic shared memory of the leaf kernel
   // tensor-core leaf (ratspn_leaf_mma.cu): 0 = not used for this call
   int leaf_mma;
+  int leaf_conv;               // main GEMM converts the fp32 inputs itself: no PREP launch, no x images, -x^2/2 added at the root
+  size_t off_sqsum;            // [Bp] -1/2 sum_f x_f^2 (leaf_conv with unit-scale Gaussian leaves), else 0
   int mma_nS, mma_nW, mma_kb;  // x^2 (region indicator) N tiles, weight N tiles, 32-feature K blocks
   size_t off_wimg, off_simg, off_cstm, off_sq, off_mflags, off_aimg;
   int act_regions[DPK_MAX_LEVELS], act_ch[DPK_MAX_LEVELS];
@@ -156,6 +159,32 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
   p->off_tab = take((size_t)p->G0 * p->kc.count * p->leaf_nch * p->leaf_chunk_floats);
   p->off_cd = take((size_t)p->G0 * p->kc.count * p->dim * p->kc.chunk);
   p->off_cst = take((size_t)p->G0 * p->kc.padded);
+  // Inference only: all product + sum levels and the root as one tensor-core kernel (DPK_TREE_MMA=0 disables it,
+  // =1 forces it for any batch size).  The backward needs every level's activations, so it keeps the layer-wise path.
+  p->tree_mma = 0; p->tree_G = 0; p->tree_tcols = 0; p->off_timg = 0; p->tree_rep_bytes = 0;
+  {
+    const int knob = env_int("DPK_TREE_MMA", -1);
+    const int Osel = (p->depth == 1) ? p->K : p->O;
+    if (knob != 0 && !(flags & (DPK_F_SAVE_ACTIVATIONS | kPlanLeafOnly)) && (batch >= kMmaMinBatch || knob == 1) &&
+        p->depth <= kTreeMaxD && ratspn_tree_instantiated(p->K, Osel)) {
+      uint32_t toff = 0, nmax = 0;
+      for (int lvl = 0; lvl < p->depth; ++lvl) {
+        const int Kin = (lvl == 0) ? p->K : p->O;
+        const int Nout = (lvl == p->depth - 1) ? p->C : p->O;
+        const uint32_t npad = (uint32_t)round_up((int64_t)Kin * Nout, 16);
+        p->tree_off[lvl] = toff; p->tree_npad[lvl] = npad;
+        toff += (uint32_t)(1 << (p->depth - 1 - lvl)) * 2u * npad * 64u;
+        nmax = std::max(nmax, npad);
+      }
+      const int Kr = (p->depth == 1) ? p->K : p->O;
+      const int tcols = nmax <= 128 ? 128 : 256;
+      const int G = 512 / tcols;
+      const size_t smem = 1024 + (((size_t)toff + 1023) & ~(size_t)1023) + (size_t)G * (16384 + 2 * p->K * 512) + 128;
+      if (nmax <= 256 && (p->C - 1) * Kr + 16 <= tcols && smem <= (size_t)max_dynamic_smem()) {
+        p->tree_mma = 1; p->tree_G = G; p->tree_tcols = tcols; p->tree_rep_bytes = toff;
+      }
+    }
+  }
   // Tensor-core leaf (all three flavours), 16-byte loadable rows.  DPK_LEAF_MMA=0 disables it, =1 forces it for any batch size (tests).
   {
     const int knob = env_int("DPK_LEAF_MMA", -1);
@@ -167,9 +196,11 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
                    ((batch >= kMmaMinBatch && wide) || knob == 1) && mma_smem <= (size_t)max_dynamic_smem())
                       ? 1 : 0;
     p->mma_nS = p->mma_nW = p->mma_kb = 0;
-    p->off_wimg = p->off_simg = p->off_cstm = p->off_sq = p->off_mflags = p->off_aimg = 0;
+    p->off_wimg = p->off_simg = p->off_cstm = p->off_sq = p->off_mflags = p->off_aimg = p->off_sqsum = 0;
+    // With the fused upper levels behind it the GEMM converts its inputs itself (DPK_LEAF_CONV=0: separate PREP launch)
+    p->leaf_conv = (p->leaf_mma && p->tree_mma && p->fwd_kind != DPK_LEAF_GAUSSIAN && env_int("DPK_LEAF_CONV", 1) != 0) ? 1 : 0;
     if (p->leaf_mma) {
-      p->mma_nS = (p->fwd_kind == kLeafGaussUnit) ? (int)ceil_div(p->G0, kMmaTileN) : 0;
+      p->mma_nS = (p->fwd_kind == kLeafGaussUnit && !p->leaf_conv) ? (int)ceil_div(p->G0, kMmaTileN) : 0;
       p->mma_nW = (int)ceil_div((int64_t)p->G0 * p->K, kMmaTileN);
       // K blocks of 32 features; a general Gaussian has a second half of them for x^2
       p->mma_kb = (int)ceil_div(p->D, kMmaKB) * (p->fwd_kind == DPK_LEAF_GAUSSIAN ? 2 : 1);
@@ -177,8 +208,12 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
       p->off_wimg = take((size_t)p->mma_nW * p->mma_kb * 2 * img_floats);
       p->off_simg = take((size_t)p->mma_nS * p->mma_kb * img_floats);   // directly behind wimg (one memset)
       p->off_cstm = take((size_t)p->G0 * p->K);
-      p->off_sq = take((size_t)p->G0 * p->Bp);
-      p->off_aimg = take((size_t)ceil_div(p->B, kMmaTileM) * p->mma_kb * 2 * img_floats);   // hi/lo fp16 split of x
+      if (!p->leaf_conv) {
+        p->off_sq = take((size_t)p->G0 * p->Bp);
+        p->off_aimg = take((size_t)ceil_div(p->B, kMmaTileM) * p->mma_kb * 2 * img_floats);   // hi/lo fp16 split of x
+      } else if (p->fwd_kind == kLeafGaussUnit) {
+        p->off_sqsum = take((size_t)p->Bp);
+      }
       p->off_mflags = take((size_t)p->Bp / 32 + 4 + 64);   // redo | wflag | unit counters | debug stats
     }
   }
@@ -201,33 +236,7 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     p->off_rlog = take(p->r_floats);
   }
   p->off_rtmp = take((size_t)p->R * p->C * p->Bp);
-  // Inference only: all product + sum levels and the root as one tensor-core kernel (DPK_TREE_MMA=0 disables it,
-  // =1 forces it for any batch size).  The backward needs every level's activations, so it keeps the layer-wise path.
-  p->tree_mma = 0; p->tree_G = 0; p->tree_tcols = 0; p->off_timg = 0; p->tree_rep_bytes = 0;
-  {
-    const int knob = env_int("DPK_TREE_MMA", -1);
-    const int Osel = (p->depth == 1) ? p->K : p->O;
-    if (knob != 0 && !(flags & DPK_F_SAVE_ACTIVATIONS) && (batch >= kMmaMinBatch || knob == 1) && p->depth <= kTreeMaxD &&
-        ratspn_tree_instantiated(p->K, Osel)) {
-      uint32_t off = 0, nmax = 0;
-      for (int lvl = 0; lvl < p->depth; ++lvl) {
-        const int Kin = (lvl == 0) ? p->K : p->O;
-        const int Nout = (lvl == p->depth - 1) ? p->C : p->O;
-        const uint32_t npad = (uint32_t)round_up((int64_t)Kin * Nout, 16);
-        p->tree_off[lvl] = off; p->tree_npad[lvl] = npad;
-        off += (uint32_t)(1 << (p->depth - 1 - lvl)) * 2u * npad * 64u;
-        nmax = std::max(nmax, npad);
-      }
-      const int Kr = (p->depth == 1) ? p->K : p->O;
-      const int tcols = nmax <= 128 ? 128 : 256;
-      const int G = 512 / tcols;
-      const size_t smem = 1024 + (((size_t)off + 1023) & ~(size_t)1023) + (size_t)G * (16384 + 2 * p->K * 512) + 128;
-      if (nmax <= 256 && (p->C - 1) * Kr + 16 <= tcols && smem <= (size_t)max_dynamic_smem()) {
-        p->tree_mma = 1; p->tree_G = G; p->tree_tcols = tcols; p->tree_rep_bytes = off;
-        p->off_timg = take((size_t)p->R * off / 4);
-      }
-    }
-  }
+  if (p->tree_mma) p->off_timg = take((size_t)p->R * p->tree_rep_bytes / 4);
   for (int l = 0; l < p->depth; ++l)
     p->off_act[l] = take((size_t)p->act_regions[l] * p->act_ch[l] * p->Bp);
   for (int l = 0; l < p->depth; ++l)

@@ -410,10 +410,13 @@ __global__ void ratspn_prep_tree_kernel(const float* __restrict__ wsoft, int P_t
   }
 }
 
+// out[b, c] = logsumexp_r part[r][c][b]  (+ the sample's -1/2 sum_f x_f^2 when the leaf GEMM left it out, see
+// ratspn_leaf_mma.cu: groups the exact leaf kernel redid carry the term inside their leaf values already)
 __global__ void tree_root_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int P, int C, int64_t B,
-                                         int64_t Bp) {
+                                         int64_t Bp, const float* __restrict__ sqsum, const int* __restrict__ redo) {
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const float add = (sqsum != nullptr && redo[b >> 5] == 0) ? sqsum[b] : 0.f;
   for (int c = 0; c < C; ++c) {
     float m = -INFINITY;
     for (int p = 0; p < P; ++p) m = fmaxf(m, part[((size_t)p * C + c) * Bp + b]);
@@ -426,7 +429,7 @@ __global__ void tree_root_combine_kernel(const float* __restrict__ part, float* 
       for (int p = 0; p < P; ++p) s += __expf(part[((size_t)p * C + c) * Bp + b] - m);
       y = m + __logf(s);
     }
-    out[(size_t)b * C + c] = y;
+    out[(size_t)b * C + c] = y + add;
   }
 }
 
@@ -499,7 +502,9 @@ int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
   }
   if (rc) return rc;
   ProfScope prof(CAT_ROOT, st);
-  tree_root_combine_kernel<<<(unsigned)ceil_div(p.B, 256), 256, 0, st>>>(ws + p.off_rtmp, out, p.R, p.C, p.B, p.Bp);
+  tree_root_combine_kernel<<<(unsigned)ceil_div(p.B, 256), 256, 0, st>>>(
+      ws + p.off_rtmp, out, p.R, p.C, p.B, p.Bp, p.off_sqsum ? ws + p.off_sqsum : nullptr,
+      reinterpret_cast<const int*>(ws + p.off_mflags));
   DPK_LAUNCH_CHECK("tree_root_combine_kernel");
   return DPK_OK;
 }
