@@ -350,7 +350,8 @@ def run_b200(args, rank, local_rank, world):
     mma = launches.get("ratspn_leaf_mma", 0) > 0
     leaf_cat = "ratspn_leaf_mma" if mma else "ratspn_leaf"
     leaf_ms = prof_ms[leaf_cat] / prof_steps     # the dominant kernel: one launch per step
-    kname = "ratspn_leaf_mma_kernel<main>" if mma else "ratspn_leaf_kernel"
+    conv = mma and launches.get("ratspn_leaf_mma_prep", 0) == 0     # the GEMM converts its inputs itself: no PREP launch
+    kname = ("ratspn_leaf_mma_kernel<conv>" if conv else "ratspn_leaf_mma_kernel<main>") if mma else "ratspn_leaf_kernel"
     algo_gbs = ALGO_BYTES_PER_SAMPLE * B / (leaf_ms * 1e-3) / 1e9
     traffic = load_traffic()
     t_kernel = None

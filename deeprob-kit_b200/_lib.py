@@ -106,6 +106,10 @@ class RatSpnEmStats(ctypes.Structure):
     ]
 
 
+class RatSpnDropout(ctypes.Structure):
+    _fields_ = [("in_rate", ctypes.c_float), ("sum_rate", ctypes.c_float), ("seed", ctypes.c_uint64)]
+
+
 class DgcProductDesc(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in ("channels", "height", "width", "out_channels", "out_height", "out_width",
                                      "pad_top", "pad_left", "stride_h", "stride_w", "dilation_h", "dilation_w",
@@ -130,6 +134,12 @@ SIGNATURES = {
                                            ctypes.POINTER(RatSpnGrads), c_vp, c_sz, c_vp]),
     "dpk_ratspn_em_statistics": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_vp, c_i64, c_vp,
                                                 ctypes.POINTER(RatSpnEmStats), c_vp, c_sz, c_vp]),
+    "dpk_dropout_draw": (c_u32, [ctypes.c_uint64, c_u32, ctypes.c_uint64]),
+    "dpk_ratspn_dropout_workspace_bytes": (c_sz, [ctypes.POINTER(RatSpnDesc), c_i64]),
+    "dpk_ratspn_forward_dropout": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_vp, c_i64, ctypes.POINTER(RatSpnDropout),
+                                                  c_vp, c_vp, c_sz, c_vp]),
+    "dpk_ratspn_backward_dropout": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_vp, c_i64, ctypes.POINTER(RatSpnDropout),
+                                                   c_vp, c_vp, ctypes.POINTER(RatSpnGrads), c_vp, c_sz, c_vp]),
     "dpk_ratspn_leaf_forward": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dpk_outer_sum_forward": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "dpk_mixture_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),

@@ -28,10 +28,10 @@ class RatSpnCall:
     """One descriptor + the tensors it borrows (kept alive for the duration of the call / autograd node)."""
 
     def __init__(self, base_layer, sum_weights: List[torch.Tensor], root_weight: Optional[torch.Tensor],
-                 out_classes: int, sum_nodes: int, repetitions: int, device):
+                 out_classes: int, sum_nodes: int, repetitions: int, device, force_scale: bool = False):
         p0, p1 = base_layer.leaf_parameters()
         self.n_leaf = 1 if p1 is None else 2          # leaf tensors among the autograd inputs
-        if p1 is not None and getattr(base_layer, "unit_scale", lambda: False)():
+        if p1 is not None and not force_scale and getattr(base_layer, "unit_scale", lambda: False)():
             p1 = None                                  # frozen scale == 1: NULL selects the unit-scale kernels
         self.keep = [_f32c(p0), _f32c(p1) if p1 is not None else None]
         self.sums = [_f32c(w) for w in sum_weights]
@@ -172,8 +172,65 @@ class _RatSpnLogProb(torch.autograd.Function):
         return (None, gx, *grads)
 
 
+class _RatSpnLogProbDropout(torch.autograd.Function):
+    """Training-mode log_prob with probabilistic dropout: dpk_ratspn_forward_dropout / dpk_ratspn_backward_dropout.
+    The masks are regenerated in the backward from the seed drawn here (one value per forward, taken from torch's
+    CPU generator so that torch.manual_seed makes a run reproducible)."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        call = model._make_call(x.device, force_scale=True)
+        batch = x.shape[0]
+        drop = _lib.RatSpnDropout()
+        drop.in_rate = float(model.in_dropout or 0.0)
+        drop.sum_rate = float(model.sum_dropout or 0.0)
+        drop.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        out = torch.empty(batch, model.out_classes, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            nbytes = _lib.lib().dpk_ratspn_dropout_workspace_bytes(ctypes.byref(call.desc), batch)
+            if nbytes == 0:
+                _lib.check(-1, "dpk_ratspn_dropout_workspace_bytes")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            rc = _lib.lib().dpk_ratspn_forward_dropout(ctypes.byref(call.desc), _ptr(x), batch, ctypes.byref(drop), _ptr(out),
+                                                       _ptr(ws), ws.numel(), _PTR(_lib.stream_ptr(x.device)))
+        _lib.check(rc, "dpk_ratspn_forward_dropout")
+        ctx.call, ctx.ws, ctx.drop = call, ws, drop
+        ctx.save_for_backward(x, out)
+        ctx.param_shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out = ctx.saved_tensors
+        call, ws = ctx.call, ctx.ws
+        need = ctx.needs_input_grad        # (model, x, *params)
+        batch = x.shape[0]
+        g = _lib.RatSpnGrads()
+        gx = torch.zeros_like(x) if need[1] else None
+        g.grad_x = gx.data_ptr() if gx is not None else None
+        grads = [torch.zeros(shape, dtype=torch.float32, device=x.device) if need[2 + i] else None
+                 for i, shape in enumerate(ctx.param_shapes)]
+        n_leaf = call.n_leaf
+        g.leaf_p0 = grads[0].data_ptr() if grads[0] is not None else None
+        if n_leaf == 2:
+            g.leaf_p1 = grads[1].data_ptr() if grads[1] is not None else None
+        for i in range(len(call.sums)):
+            t = grads[n_leaf + i]
+            g.sum_weight[i] = t.data_ptr() if t is not None else None
+        g.root_weight = grads[-1].data_ptr() if grads[-1] is not None else None
+        grad_out = _f32c(grad_out)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_ratspn_backward_dropout(ctypes.byref(call.desc), _ptr(x), batch, ctypes.byref(ctx.drop),
+                                                        _ptr(out), _ptr(grad_out), ctypes.byref(g), _ptr(ws), ws.numel(),
+                                                        _PTR(_lib.stream_ptr(x.device)))
+        _lib.check(rc, "dpk_ratspn_backward_dropout")
+        return (None, gx, *grads)
+
+
 def ratspn_log_prob(model, x: torch.Tensor) -> torch.Tensor:
     x = _check_input(x, model.in_features, "RatSpn.forward")
+    if model.training and (model.in_dropout is not None or model.sum_dropout is not None):
+        return _RatSpnLogProbDropout.apply(model, x, *model._kernel_parameters())
     return _RatSpnLogProb.apply((model, torch.is_grad_enabled()), x, *model._kernel_parameters())
 
 

@@ -71,7 +71,16 @@ class SpatialGaussianLayer(_SpatialShape, nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training and self.dropout is not None:
-            raise NotImplementedError("input dropout is not implemented in the CUDA path; use dropout=None or .eval()")
+            # layers/dgcspn.py:113-115: NaN dropout on the per-channel log-densities (B, K, C_in, H, W) before
+            # nan_to_num and the sum over the input channels, i.e. a dropped (b, k, c, h, w) term contributes 0.
+            # One kernel call per input channel (C_in is 1 or 3) keeps every term separately maskable; the
+            # Bernoulli draws come from torch's generator exactly like the reference's `torch.rand_like`.
+            out = None
+            for c in range(x.shape[1]):
+                term = _dgc_engine.leaf(x[:, c:c + 1].contiguous(), self.loc[:, c:c + 1], self.scale[:, c:c + 1])
+                term = term.masked_fill(torch.rand_like(term) < self.dropout, 0.0)
+                out = term if out is None else out + term
+            return out
         return _dgc_engine.leaf(x, self.loc, self.scale)
 
 
@@ -138,7 +147,9 @@ class SpatialSumLayer(_SpatialShape, nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training and self.dropout is not None:
-            raise NotImplementedError("sum dropout is not implemented in the CUDA path; use dropout=None or .eval()")
+            # layers/dgcspn.py:297-299: x[torch.rand_like(x) < dropout] = -inf in front of the mixture (out of place
+            # here: autograd-friendly; a dropped input gets no gradient, an all-dropped pixel gives -inf)
+            x = x.masked_fill(torch.rand_like(x) < self.dropout, float("-inf"))
         return _dgc_engine.mixture(x, self.weight)
 
 

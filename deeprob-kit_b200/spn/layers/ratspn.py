@@ -201,8 +201,8 @@ class SumLayer(nn.Module):
         dirichlet_(self.weight, alpha=1.0)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.training and self.dropout is not None:
-            raise NotImplementedError("stand-alone sum layer call with dropout: call the model instead")
+        if self.training and self.dropout is not None:   # layers/ratspn.py:370-372 (the stand-alone layer has no backward)
+            x = x.masked_fill(torch.rand_like(x) < self.dropout, float("-inf"))
         return _engine.mixture_forward(x, self.weight)
 
     @torch.no_grad()

@@ -96,9 +96,10 @@ class RatSpn(ProbabilisticModel):
         leaf = (p0,) if p1 is None else (p0, p1)
         return (*leaf, *(layer.weight for layer in self._sum_layers()), self.root_layer.weight)
 
-    def _make_call(self, device) -> "_engine.RatSpnCall":
+    def _make_call(self, device, force_scale: bool = False) -> "_engine.RatSpnCall":
         return _engine.RatSpnCall(self.base_layer, [layer.weight for layer in self._sum_layers()],
-                                  self.root_layer.weight, self.out_classes, self.rg_sum, self.rg_repetitions, device)
+                                  self.root_layer.weight, self.out_classes, self.rg_sum, self.rg_repetitions, device,
+                                  force_scale)
 
     def _workspace(self, call, batch: int, flags: int, device, private: bool):
         """(workspace, extra flags).  Inference reuses one grow-only buffer per (device, stream); when neither the
@@ -125,12 +126,9 @@ class RatSpn(ProbabilisticModel):
 
     # ---- API ---------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """Log-likelihood (B, out_classes) given evidence x (B, in_features); NaN = marginalised."""
-        if self.training and (self.in_dropout is not None or self.sum_dropout is not None):
-            raise NotImplementedError(
-                "probabilistic dropout inside the fused CUDA path is not implemented yet; "
-                "use in_dropout=None/sum_dropout=None or call .eval()"
-            )
+        """Log-likelihood (B, out_classes) given evidence x (B, in_features); NaN = marginalised.  In training mode
+        with `in_dropout` / `sum_dropout` set, the probabilistic dropout of the reference layers
+        (layers/ratspn.py:98-100, :370-372) is applied with draws from a counter-based generator (csrc/ratspn_dropout.cu)."""
         return _engine.ratspn_log_prob(self, x)
 
     def em_statistics(self, x: torch.Tensor):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DPK_ABI_VERSION 1
+#define DPK_ABI_VERSION 2
 #define DPK_MAX_LEVELS 16
 
 #define DPK_OK 0
@@ -121,6 +121,29 @@ int dpk_ratspn_backward(const dpk_ratspn_desc* desc, const float* x, int64_t bat
 int dpk_ratspn_em_statistics(const dpk_ratspn_desc* desc, const float* x, int64_t batch,
                              const float* out, const dpk_ratspn_em_stats* stats, void* workspace,
                              size_t workspace_bytes, void* stream);
+
+/* Training mode with probabilistic dropout (deeprob/spn/layers/ratspn.py:98-100: NaN dropout on the per-dimension
+ * leaf log-densities (B, G0, K, dim); :370-372: -inf dropout on every product layer output (B, P, K^2) in front of a
+ * sum layer; the root has none).  The reference draws from torch's RNG stream (`torch.rand_like`), which no fused
+ * kernel can reproduce: here every Bernoulli draw is a pure function of (seed, stream, element index) -- the
+ * backward regenerates it -- so parity with the reference is distributional, and exact against the oracle with
+ * the same draws injected (dpk_dropout_draw exposes the generator to the tests).  An element is dropped when
+ * dpk_dropout_draw(seed, stream, index) < rate * 2^24; stream 0 = leaf elements ((b*G0+g)*K+k)*dim+d, stream 1+e =
+ * sum level e elements (b*P_e+p)*Kin^2+ij. */
+typedef struct dpk_ratspn_dropout {
+  float in_rate;   /* RegionGraphLayer dropout in [0, 1), 0 = none */
+  float sum_rate;  /* SumLayer dropout in [0, 1), 0 = none */
+  uint64_t seed;   /* one fresh value per forward; the same value for its backward */
+} dpk_ratspn_dropout;
+uint32_t dpk_dropout_draw(uint64_t seed, uint32_t stream, uint64_t index); /* host: uniform 24-bit integer */
+size_t dpk_ratspn_dropout_workspace_bytes(const dpk_ratspn_desc* desc, int64_t batch);
+int dpk_ratspn_forward_dropout(const dpk_ratspn_desc* desc, const float* x, int64_t batch,
+                               const dpk_ratspn_dropout* drop, float* out, void* workspace, size_t workspace_bytes,
+                               void* stream);
+/* gradients as in dpk_ratspn_backward (accumulated into zero-filled buffers); `workspace` from the forward */
+int dpk_ratspn_backward_dropout(const dpk_ratspn_desc* desc, const float* x, int64_t batch,
+                                const dpk_ratspn_dropout* drop, const float* out, const float* grad_out,
+                                const dpk_ratspn_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stand-alone layers with the reference layouts (used by the nn.Module layer classes). */
 /* RegionGraphLayer.forward: out (B, G0, K) */

@@ -14,13 +14,17 @@ import torch.nn.functional as F
 _LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
 
 
-def spatial_gaussian(x, loc, scale, clean_nan=False):
-    """SpatialGaussianLayer.forward, eval mode (layers/dgcspn.py:101-120): (B,Cin,H,W)->(B,K,H,W)."""
+def spatial_gaussian(x, loc, scale, clean_nan=False, drop=None):
+    """SpatialGaussianLayer.forward (layers/dgcspn.py:101-120): (B,Cin,H,W)->(B,K,H,W).  `drop` (bool,
+    (B,K,Cin,H,W)) restates the training-mode dropout of :113-115 (NaN on the per-channel log-densities) with
+    injected Bernoulli draws."""
     v = x.unsqueeze(1)
     missing = torch.isnan(v)
     if clean_nan:           # same values; autograd then gives the gradient of the marginalised LL (see ratspn_oracle)
         v = torch.where(missing, torch.zeros_like(v), v)
     ll = -((v - loc) ** 2) / (2 * scale ** 2) - scale.log() - _LOG_SQRT_2PI   # Normal.log_prob  (:110)
+    if drop is not None:
+        ll = torch.where(drop, torch.full_like(ll, float("nan")), ll)          # :113-115
     ll = torch.nan_to_num(ll)                                                  # :117
     if clean_nan:
         ll = torch.where(missing, torch.zeros_like(ll), ll)
@@ -53,8 +57,10 @@ def spatial_product(x, pad, weight, stride, dilation, groups):
     return F.conv2d(F.pad(x, pad), weight.to(x.dtype), stride=stride, dilation=dilation, groups=groups)
 
 
-def spatial_sum(x, weight):
-    """SpatialSumLayer.forward, eval mode (layers/dgcspn.py:301-303)."""
+def spatial_sum(x, weight, drop=None):
+    """SpatialSumLayer.forward (layers/dgcspn.py:289-303); `drop` (bool, like x) = the -inf dropout of :297-299."""
+    if drop is not None:
+        x = torch.where(drop, torch.full_like(x, float("-inf")), x)
     return torch.logsumexp(x.unsqueeze(1) + torch.log_softmax(weight, dim=1), dim=2)
 
 
@@ -106,14 +112,17 @@ class DgcSpnOracle:
         self.sum_weights = [w.double() for w in self.sum_weights]
         return self
 
+    leaf_drop = None    # injected training-mode dropout draws (see spatial_gaussian / spatial_sum)
+    sum_drops = None
+
     def log_prob(self, x, keep=None):
-        h = spatial_gaussian(x, self.loc, self.scale, self.clean_nan)
+        h = spatial_gaussian(x, self.loc, self.scale, self.clean_nan, self.leaf_drop)
         if keep is not None:
             keep.append(h)
         for i, p in enumerate(self.products):
             h = spatial_product(h, p["pad"], p["weight"], p["stride"], p["dilation"], p["groups"])
             if i < len(self.sum_weights):
-                h = spatial_sum(h, self.sum_weights[i])
+                h = spatial_sum(h, self.sum_weights[i], self.sum_drops[i] if self.sum_drops is not None else None)
         return spatial_root(h, self.root_weight)
 
     def grads(self, x, grad_out, clean_nan=True):

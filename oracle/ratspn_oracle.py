@@ -76,8 +76,14 @@ def bernoulli_log_density(v: torch.Tensor, logits: torch.Tensor) -> torch.Tensor
     return -torch.nn.functional.binary_cross_entropy_with_logits(lg, vv, reduction="none")
 
 
-def leaf_layer(x, mask, pad_mask, kind: str, params: Dict[str, torch.Tensor], clean_nan: bool = False) -> torch.Tensor:
-    """RegionGraphLayer.forward, eval mode (deeprob/spn/layers/ratspn.py:87-108): (B,D)->(B,G0,K).
+def leaf_layer(x, mask, pad_mask, kind: str, params: Dict[str, torch.Tensor], clean_nan: bool = False,
+               drop: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RegionGraphLayer.forward (deeprob/spn/layers/ratspn.py:87-108): (B,D)->(B,G0,K).
+
+    `drop` (bool, (B,G0,K,dim)) restates the training-mode input dropout of :98-100,
+    `x[torch.rand_like(x) < self.dropout] = np.nan` on the per-dimension log-densities, with the Bernoulli draws
+    injected instead of taken from torch's RNG stream (a fused kernel cannot reproduce that stream; the tests
+    inject the masks the CUDA path derives from its counter-based generator).
 
     `clean_nan=True` evaluates marginalised (NaN) inputs at 0 and masks their terms with `where`: the
     values are identical, but autograd then yields the gradient of the marginalised likelihood
@@ -93,6 +99,8 @@ def leaf_layer(x, mask, pad_mask, kind: str, params: Dict[str, torch.Tensor], cl
         ll = bernoulli_log_density(v, params["logits"])
     else:
         raise ValueError(kind)
+    if drop is not None:
+        ll = torch.where(drop, torch.full_like(ll, float("nan")), ll) # :98-100 (out of place: autograd-friendly)
     ll = torch.nan_to_num(ll)                                         # :103  NaN->0, +-inf->+-FLT_MAX
     if clean_nan:
         ll = torch.where(missing, torch.zeros_like(ll), ll)
@@ -108,8 +116,11 @@ def product_layer(x: torch.Tensor) -> torch.Tensor:
     return out.reshape(x.shape[0], x.shape[1] // 2, x.shape[2] ** 2)
 
 
-def sum_layer(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """SumLayer.forward, eval mode (ratspn.py:363-378): (B,P,Kin)+(P,O,Kin) -> (B,P,O)."""
+def sum_layer(x: torch.Tensor, weight: torch.Tensor, drop: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SumLayer.forward (ratspn.py:363-378): (B,P,Kin)+(P,O,Kin) -> (B,P,O).  `drop` (bool, (B,P,Kin)) restates the
+    training-mode dropout of :370-372, `x[torch.rand_like(x) < self.dropout] = -np.inf`, with injected draws."""
+    if drop is not None:
+        x = torch.where(drop, torch.full_like(x, float("-inf")), x)
     w = torch.log_softmax(weight, dim=2)
     return torch.logsumexp(x.unsqueeze(2) + w, dim=3)
 
@@ -160,17 +171,20 @@ class RatSpnOracle:
         self.root_weight = self.root_weight.double()
         return self
 
-    def leaf(self, x):
-        return leaf_layer(x, self.mask, self.pad_mask, self.kind, self.params, self.clean_nan)
+    def leaf(self, x, drop=None):
+        return leaf_layer(x, self.mask, self.pad_mask, self.kind, self.params, self.clean_nan, drop)
+
+    leaf_drop = None    # injected training-mode dropout masks (see leaf_layer / sum_layer): (B,G0,K,dim) bool
+    sum_drops = None    # list over the sum levels of (B,P,Kin) bool
 
     def log_prob(self, x: torch.Tensor, keep: Optional[list] = None) -> torch.Tensor:
-        h = self.leaf(x)
+        h = self.leaf(x, self.leaf_drop)
         if keep is not None:
             keep.append(h)
         for lvl in range(self.depth):                                 # Product, Sum, ..., Product
             h = product_layer(h)
             if lvl < self.depth - 1:
-                h = sum_layer(h, self.sum_weights[lvl])
+                h = sum_layer(h, self.sum_weights[lvl], self.sum_drops[lvl] if self.sum_drops is not None else None)
                 if keep is not None:
                     keep.append(h)
         return root_layer(h, self.root_weight)

@@ -13,12 +13,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def short_name(full):
-    """`dpk::<unnamed>::ratspn_leaf_mma_kernel<(bool)0, (bool)0>(args)` -> ratspn_leaf_mma_kernel<main>"""
-    m = re.search(r"(\w+)(<[^(]*>)?\s*\(", full)
+    """`void dpk::<unnamed>::ratspn_leaf_mma_kernel<0, 0, 1>(args)` -> ratspn_leaf_mma_kernel<conv>"""
+    tail = full.split("unnamed>::", 1)[1] if "unnamed>::" in full else full
+    m = re.match(r"\s*(?:void\s+)?(?:\w+::)*([A-Za-z_]\w*)\s*(<.*>)?\s*\(", tail)
     name = m.group(1) if m else full
     targs = (m.group(2) or "") if m else ""
     if name == "ratspn_leaf_mma_kernel":
-        return name + ("<prep>" if re.match(r"<\s*(\(bool\))?\s*(1|true)\b", targs) else "<main>")
+        flags = re.findall(r"(?:\(bool\))?\s*(1|0|true|false)", targs)
+        on = [f in ("1", "true") for f in flags] + [False] * 3
+        return name + ("<prep>" if on[0] else "<conv>" if on[2] else "<main>")
     return name
 
 

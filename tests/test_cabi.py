@@ -26,7 +26,7 @@ def test_header_symbols_are_bound_and_exported():
 
 def test_version_and_error_convention():
     lib = _lib.lib()
-    assert lib.dpk_abi_version() == 1
+    assert lib.dpk_abi_version() == 2
     # argument validation happens on the host before any CUDA call: usable without a GPU
     desc = _lib.RatSpnDesc()
     assert lib.dpk_ratspn_workspace_bytes(ctypes.byref(desc), 8, 0) == 0
