@@ -234,6 +234,43 @@ def ratspn_log_prob(model, x: torch.Tensor) -> torch.Tensor:
     return _RatSpnLogProb.apply((model, torch.is_grad_enabled()), x, *model._kernel_parameters())
 
 
+def ratspn_mpe(model, x: torch.Tensor, y: Optional[torch.Tensor]) -> torch.Tensor:
+    """RatSpn.mpe: forward keeping every level's log-likelihoods, then the top-down kernel (dpk_ratspn_mpe)."""
+    x = _check_input(x, model.in_features, "RatSpn.mpe")
+    call = model._make_call(x.device)
+    batch, dev = x.shape[0], x.device
+    out = torch.empty(batch, model.out_classes, dtype=torch.float32, device=dev)
+    filled = torch.empty_like(x)
+    yi = y.to(device=dev, dtype=torch.int32).contiguous() if y is not None else None
+    with torch.cuda.device(dev):
+        ws = call.workspace(batch, _lib.F_SAVE_ACTIVATIONS, dev)
+        sp = _PTR(_lib.stream_ptr(dev))
+        rc = _lib.lib().dpk_ratspn_forward(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(ws), ws.numel(),
+                                           _lib.F_SAVE_ACTIVATIONS, sp)
+        _lib.check(rc, "dpk_ratspn_forward")
+        rc = _lib.lib().dpk_ratspn_mpe(ctypes.byref(call.desc), _ptr(x), batch, _ptr(out), _ptr(yi), _ptr(filled), _ptr(ws),
+                                       ws.numel(), sp)
+    _lib.check(rc, "dpk_ratspn_mpe")
+    return filled
+
+
+def ratspn_sample(model, n_samples: int, y: Optional[torch.Tensor], device) -> torch.Tensor:
+    """RatSpn.sample: ancestral sampling kernel (dpk_ratspn_sample); the seed comes from torch's CPU generator."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("RatSpn.sample: deeprob_kit_b200 runs on CUDA devices only; there is no CPU path")
+    call = model._make_call(device, force_scale=True)
+    out = torch.empty(n_samples, model.in_features, dtype=torch.float32, device=device)
+    yi = y.to(device=device, dtype=torch.int32).contiguous() if y is not None else None
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    with torch.cuda.device(device):
+        ws = call.workspace(n_samples, _lib.F_SAVE_ACTIVATIONS, device)
+        rc = _lib.lib().dpk_ratspn_sample(ctypes.byref(call.desc), n_samples, _ptr(yi), seed, _ptr(out), _ptr(ws), ws.numel(),
+                                          _PTR(_lib.stream_ptr(device)))
+    _lib.check(rc, "dpk_ratspn_sample")
+    return out
+
+
 def ratspn_em_statistics(model, x: torch.Tensor):
     """E-step sufficient statistics of a batch (dict of tensors; see include/deeprob_b200.h)."""
     x = _check_input(x, model.in_features, "RatSpn.em_statistics")

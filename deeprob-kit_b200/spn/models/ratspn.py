@@ -137,32 +137,39 @@ class RatSpn(ProbabilisticModel):
 
     @torch.no_grad()
     def mpe(self, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
-        inputs, n = x, x.shape[0]
-        lls = []
-        h = self.base_layer(x)
-        for layer in self.layers:
-            lls.append(h)
-            h = layer(h)
+        """Maximum-a-posteriori completion of the NaN entries of x (models/ratspn.py:124-160): one forward that keeps
+        every level's log-likelihoods, then one top-down kernel (csrc/ratspn_topdown.cu)."""
         if self.out_classes == 1:
-            y = torch.zeros(n, dtype=torch.long, device=x.device)
-        elif y is None:
-            y = torch.argmax(self.root_layer(h), dim=1)
-        group, offset = self.root_layer.mpe(h, y)
-        for i in range(len(self.layers) - 1, -1, -1):
-            group, offset = self.layers[i].mpe(lls[i], group, offset)
-        return self.base_layer.mpe(inputs, group, offset)
+            y = None
+        return _engine.ratspn_mpe(self, x, y)
 
     @torch.no_grad()
     def sample(self, n_samples: int, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Ancestral samples (models/ratspn.py:162-182), one kernel (csrc/ratspn_topdown.cu)."""
         device = self.root_layer.weight.device
         if self.out_classes == 1:
-            y = torch.zeros(n_samples, dtype=torch.long, device=device)
+            y = None
         elif y is None:
-            y = torch.randint(self.out_classes, [n_samples], device=device)
-        group, offset = self.root_layer.sample(y)
-        for i in range(len(self.layers) - 1, -1, -1):
-            group, offset = self.layers[i].sample(group, offset)
-        return self.base_layer.sample(group, offset)
+            y = torch.randint(self.out_classes, [n_samples])
+        return _engine.ratspn_sample(self, n_samples, y, device)
+
+    def mpe_layerwise(self, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference's layer-by-layer index walk (same result as `mpe`; kept for the stand-alone layer API)."""
+        with torch.no_grad():
+            inputs, n = x, x.shape[0]
+            lls = []
+            h = self.base_layer(x)
+            for layer in self.layers:
+                lls.append(h)
+                h = layer(h)
+            if self.out_classes == 1:
+                y = torch.zeros(n, dtype=torch.long, device=x.device)
+            elif y is None:
+                y = torch.argmax(self.root_layer(h), dim=1)
+            group, offset = self.root_layer.mpe(h, y)
+            for i in range(len(self.layers) - 1, -1, -1):
+                group, offset = self.layers[i].mpe(lls[i], group, offset)
+            return self.base_layer.mpe(inputs, group, offset)
 
     def loss(self, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.out_classes == 1:

@@ -145,6 +145,18 @@ int dpk_ratspn_backward_dropout(const dpk_ratspn_desc* desc, const float* x, int
                                 const dpk_ratspn_dropout* drop, const float* out, const float* grad_out,
                                 const dpk_ratspn_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Top-down passes (deeprob/spn/models/ratspn.py:124-182 RatSpn.mpe / RatSpn.sample and the layers' mpe / sample
+ * methods, deeprob/spn/layers/ratspn.py:118-157,288-330,380-417,460-490), one thread per sample.
+ * dpk_ratspn_mpe: `workspace` is the one a dpk_ratspn_forward with DPK_F_SAVE_ACTIVATIONS filled for the same x,
+ * `out` its result; y (B) int32 classes or NULL (= argmax of out, C > 1); filled (B, D) = x with every NaN entry
+ * replaced by the mode of the leaf channel the maximising path selects.  Ties resolve like torch.argmax.
+ * dpk_ratspn_sample: ancestral samples (n, D); y (n) int32 classes or NULL (class 0); draws come from the
+ * counter-based generator (seed); `workspace` of dpk_ratspn_workspace_bytes(desc, n, DPK_F_SAVE_ACTIVATIONS). */
+int dpk_ratspn_mpe(const dpk_ratspn_desc* desc, const float* x, int64_t batch, const float* out, const int32_t* y,
+                   float* filled, void* workspace, size_t workspace_bytes, void* stream);
+int dpk_ratspn_sample(const dpk_ratspn_desc* desc, int64_t n_samples, const int32_t* y, uint64_t seed, float* samples,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Stand-alone layers with the reference layouts (used by the nn.Module layer classes). */
 /* RegionGraphLayer.forward: out (B, G0, K) */
 int dpk_ratspn_leaf_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,

@@ -66,6 +66,25 @@ def make_ratspn():
         print("ratspn", name, "ll[:3]=", rec["ll"].reshape(-1)[:3])
 
 
+def make_mpe():
+    """Reference RatSpn.mpe outputs (CPU; the reference builds its index tensors on the CPU)."""
+    from deeprob.spn.models.ratspn import GaussianRatSpn, BernoulliRatSpn
+    rec = {}
+    for name, cfg in pg.MPE_CASES.items():
+        cls = GaussianRatSpn if cfg["kind"] == "gaussian" else BernoulliRatSpn
+        torch.manual_seed(0)
+        model = cls(**pg.ratspn_ctor_kwargs(cfg)).eval()
+        model.load_state_dict(pg.ratspn_fill_state(model.state_dict(), cfg))
+        x, _ = pg.ratspn_inputs(cfg)
+        with torch.no_grad():
+            rec[name] = _np(model.mpe(x))
+            if cfg["out_classes"] > 1:
+                y = torch.arange(x.shape[0]) % cfg["out_classes"]
+                rec[name + ".y"] = _np(model.mpe(x, y))
+        print("mpe", name, rec[name].shape, "NaN left:", int(np.isnan(rec[name]).sum()))
+    np.savez_compressed(os.path.join(GOLDEN, "ratspn_mpe.npz"), **rec)
+
+
 def make_dgcspn():
     from deeprob.spn.models.dgcspn import DgcSpn
     for name, cfg in pg.DGCSPN_CASES.items():
@@ -137,6 +156,8 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     if what in ("ratspn", "all"):
         make_ratspn()
+    if what in ("mpe", "all"):
+        make_mpe()
     if what in ("dgcspn", "all") and "make_dgcspn" in globals():
         globals()["make_dgcspn"]()
     if what in ("flows", "all") and "make_flows" in globals():

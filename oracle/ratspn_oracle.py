@@ -189,6 +189,53 @@ class RatSpnOracle:
                     keep.append(h)
         return root_layer(h, self.root_weight)
 
+    def mpe(self, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """RatSpn.mpe (models/ratspn.py:124-160): bottom-up pass keeping the input of every layer, then top-down
+        RootLayer.mpe (layers/ratspn.py:460-473: argmax over all (partition, i*K+j) of x + log_softmax(W)[y]),
+        ProductLayer.mpe (:288-330: (group, i*K+j) -> (2*group, i), (2*group+1, j)), SumLayer.mpe (:380-396: argmax
+        over the inputs of the selected sum node of x[group] + log_softmax(W[group, o])) and the leaf's mode of the
+        selected channel (:118-137; Normal mean :212-213, Bernoulli [p >= 1/2] :245-247) written to the NaN entries.
+        The last step is restated as an explicit scatter through the gather table: identical to the reference's
+        gather(inv_mask) for pad == 0; for pad > 0 the reference's unpad step (:82-84) keeps the PADDED entries --
+        a bug this restatement (and the CUDA path) does not reproduce."""
+        h = self.leaf(x)
+        inputs = []                                   # inputs of the sum layers, bottom-up
+        for lvl in range(self.depth):
+            h = product_layer(h)
+            if lvl < self.depth - 1:
+                inputs.append(h)
+                h = sum_layer(h, self.sum_weights[lvl])
+        n = x.shape[0]
+        rows = torch.arange(n).unsqueeze(1)
+        if self.C == 1:
+            y = torch.zeros(n, dtype=torch.long)
+        elif y is None:
+            y = torch.argmax(root_layer(h, self.root_weight), dim=1)
+        kin2 = h.shape[2]
+        idx = torch.argmax(h.flatten(1) + torch.log_softmax(self.root_weight, dim=1)[y], dim=1, keepdim=True)
+        group, offset = torch.div(idx, kin2, rounding_mode="floor"), torch.remainder(idx, kin2)
+        for lvl in range(self.depth - 1, -1, -1):
+            # product layer `lvl`: split every (partition, i*K+j) into its two child regions
+            k = int(round(math.sqrt(kin2)))
+            group = torch.stack([group * 2, group * 2 + 1], dim=2).flatten(1)
+            offset = torch.stack([torch.div(offset, k, rounding_mode="floor"), torch.remainder(offset, k)], dim=2).flatten(1)
+            if lvl > 0:
+                xin = inputs[lvl - 1][rows, group]                                        # (n, regions, Kin^2)
+                w = torch.log_softmax(self.sum_weights[lvl - 1][group, offset], dim=2)
+                offset = torch.argmax(xin + w, dim=2)
+                kin2 = xin.shape[2]
+        mode = self.params["loc"] if self.kind == "gaussian" else (torch.sigmoid(self.params["logits"]) >= 0.5).to(x.dtype)
+        out = x.clone()
+        picked = mode[group, offset]                                                     # (n, 2^depth, dim)
+        for r in range(group.shape[1]):
+            for b in range(n):
+                g = int(group[b, r])
+                feats = list(self.leaf_regions[g])
+                vals = picked[b, r, :len(feats)]
+                cur = out[b, feats]
+                out[b, feats] = torch.where(torch.isnan(cur), vals.to(out.dtype), cur)
+        return out
+
     def log_prob_chunked(self, x: torch.Tensor, chunk: int = 1024) -> torch.Tensor:
         """The leaf temporary is (B,G0,K,dim) floats (501 KB/sample at D=784,R=16,K=10) -> chunk the batch."""
         return torch.cat([self.log_prob(x[i:i + chunk]) for i in range(0, x.shape[0], chunk)], 0)

@@ -35,6 +35,19 @@ RATSPN_CASES = {
 }
 RATSPN_SEED = 42          # region-graph random_state used by every case
 
+# MPE completion cases (reference RatSpn.mpe, models/ratspn.py:124-160).  All have pad == 0 (D % 2^depth == 0):
+# with padding the reference's unpad step keeps the padded entries (layers/ratspn.py:82-84) and is no ground truth.
+MPE_CASES = {
+    "mpe_gauss": dict(kind="gaussian", in_features=16, rg_depth=2, rg_repetitions=3, rg_batch=3, rg_sum=2,
+                      out_classes=3, batch=40, nan_frac=0.4, optimize_scale=True),
+    "mpe_bern": dict(kind="bernoulli", in_features=32, rg_depth=3, rg_repetitions=2, rg_batch=4, rg_sum=3,
+                     out_classes=1, batch=33, nan_frac=0.5, binary=True),
+    "mpe_d1": dict(kind="gaussian", in_features=8, rg_depth=1, rg_repetitions=4, rg_batch=3, rg_sum=2,
+                   out_classes=2, batch=20, nan_frac=0.3, optimize_scale=False),
+    "mpe_784": dict(kind="gaussian", in_features=784, rg_depth=3, rg_repetitions=16, rg_batch=10, rg_sum=10,
+                    out_classes=1, batch=24, nan_frac=0.5, optimize_scale=False),
+}
+
 
 def ratspn_ctor_kwargs(cfg):
     kw = {k: cfg[k] for k in ("in_features", "rg_depth", "rg_repetitions", "rg_batch", "rg_sum", "out_classes")}
