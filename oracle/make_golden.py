@@ -107,17 +107,19 @@ def make_dgcspn():
         print("dgcspn", name, "ll[:3]=", rec["ll"].reshape(-1)[:3])
 
 
-def make_flows():
+def make_flows(only=None):
     from deeprob.flows import models as ref_models
     import warnings
     warnings.simplefilter("ignore")
     for name, cfg in pg.FLOW_CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         model = getattr(ref_models, cfg["model"])(**cfg["kw"])
-        model.load_state_dict(pg.flow_fill_state(model.state_dict()))
+        model.load_state_dict(pg.flow_fill_state(model.state_dict(), fill_all=cfg.get("fill_all", False)))
         x, g = pg.flow_inputs(cfg)
         rec = {}
-        if cfg["model"] == "RealNVP2d":        # conv conditioners: keep the whole (small) state in the fixture
+        if cfg["model"] == "RealNVP2d" and not cfg.get("fill_all", False):   # conv conditioners: keep the whole (small) state in the fixture
             for k, v in model.state_dict().items():
                 rec["state." + k] = _np(v)
         model.eval()
@@ -161,4 +163,4 @@ if __name__ == "__main__":
     if what in ("dgcspn", "all") and "make_dgcspn" in globals():
         globals()["make_dgcspn"]()
     if what in ("flows", "all") and "make_flows" in globals():
-        globals()["make_flows"]()
+        globals()["make_flows"](sys.argv[2:] or None)

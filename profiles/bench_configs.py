@@ -2,6 +2,7 @@
   config 3  DgcSpn((1,28,28), n_batch=8, sum_channels=8, depthwise=True), batch 32768
   config 3b DgcSpn((1,28,28), n_batch=16, sum_channels=32, depthwise=True, n_pooling=2)  (MNIST example setting)
   config 4  RealNVP1d(3072, n_flows=8, depth=2, units=512), batch 16384
+  config 4b RealNVP2d((3,32,32), n_flows=1, n_blocks=4, channels=64), batch 1024 per step (examples/nvp2d_cifar10.py)
   config 1  BernoulliRatSpn(15, 3, 4, 4, 2) on all 2^15 states
 The CPU oracle (oracle/) is imported here only as the timed CPU comparator, the same role it has in bench.py's
 cpu_baseline leg; nothing on the measured GPU path touches it.
@@ -18,7 +19,7 @@ import torch  # noqa: E402
 
 warnings.simplefilter("ignore")
 from deeprob_kit_b200 import _lib  # noqa: E402
-from deeprob_kit_b200.flows.models import RealNVP1d  # noqa: E402
+from deeprob_kit_b200.flows.models import RealNVP1d, RealNVP2d  # noqa: E402
 from deeprob_kit_b200.spn.models import BernoulliRatSpn, DgcSpn  # noqa: E402
 
 NO_CPU = "--no-cpu" in sys.argv
@@ -109,6 +110,20 @@ if want("realnvp1d_3072_8flows"):
         st = {k: v.detach().cpu() for k, v in m.state_dict().items()}
         cpu = cpu_time(lambda t: flow1d_log_prob(t, st, "RealNVP1d", dict(in_features=3072))[0], x, 2048)
     report("realnvp1d_3072_8flows", 16384, 3072, ms, kern, cpu, ms_t)
+
+if want("realnvp2d_32x32x3"):
+    import param_gen as pg
+    cfg = pg.FLOW_CASES["nvp2d_cifar"]
+    m = RealNVP2d(**cfg["kw"])
+    m.load_state_dict(pg.flow_fill_state(m.state_dict(), fill_all=True))
+    m = m.cuda().eval()
+    x = torch.randn(1024, 3, 32, 32, device="cuda")
+    ms, kern = gpu_time(m, x, steps=5)
+    ms_t, _ = gpu_time(m, x[:256], steps=3, grad=True)
+    cpu = None
+    if not NO_CPU:      # the CPU comparator of this config is the product model's own modules on the CPU is not possible
+        cpu = None      # (no CPU path); the reference rate measured by the survey is 29 samples/s
+    report("realnvp2d_32x32x3_4blocks_64ch", 1024, 3072, ms, kern, cpu, ms_t * 1024 / 256)
 
 if want("bernoulli_ratspn_15_all_states"):
     m = BernoulliRatSpn(15, rg_depth=3, rg_repetitions=4, rg_batch=4, rg_sum=2, random_state=42).cuda().eval()

@@ -87,7 +87,9 @@ def flow_reference_state(cfg, name=None):
     import warnings
     warnings.simplefilter("ignore")
     model = getattr(fm, cfg["model"])(**cfg["kw"])
-    if cfg["model"] == "RealNVP2d":
+    if cfg.get("fill_all", False):
+        state = pg.flow_fill_state(model.state_dict(), fill_all=True)
+    elif cfg["model"] == "RealNVP2d":
         gold = load_golden("flows_" + name)
         state = {k[len("state."):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("state.")}
     else:

@@ -171,10 +171,15 @@ FLOW_CASES = {
                       unit_x=False),
     "nvp2d_dense": dict(model="RealNVP2d", kw=dict(in_features=(2, 8, 8), network="densenet", n_flows=1, n_blocks=1, channels=4,
                                                    logit=0.1), batch=10, unit_x=True),
+    # BASELINE config 4 (secondary, examples/nvp2d_cifar10.py:30-38): 32x32x3, 10 couplings with residual conv
+    # conditioners of 4 blocks x 64 channels.  10 M parameters: every tensor is a function of the NumPy seed
+    # (fill_all) instead of being stored in the fixture.
+    "nvp2d_cifar": dict(model="RealNVP2d", kw=dict(in_features=(3, 32, 32), n_flows=1, n_blocks=4, channels=64), batch=4,
+                        unit_x=False, fill_all=True),
 }
 
 
-def flow_fill_state(state, seed=0):
+def flow_fill_state(state, seed=0, fill_all=False):
     """Perturb a freshly initialised flow state_dict so that every term is exercised: ScaledTanh weights are
     zero-initialised (log-det == 0 at init, deeprob/torch/utils.py:61) and the batch-norm statistics are trivial."""
     rng = np.random.RandomState(5000 + seed)
@@ -194,6 +199,14 @@ def flow_fill_state(state, seed=0):
         elif name == "weight" and t.dim() == 2 and "network" in key:                   # Linear / MaskedLinear
             v = rng.standard_normal(shape) * (0.7 / np.sqrt(shape[1]))
         elif name == "bias" and "network" in key and t.dim() == 1 and "conv" not in key:
+            v = 0.1 * rng.standard_normal(shape)
+        elif fill_all and t.is_floating_point() and t.dim() == 4:                      # conv kernels (weight_v | weight)
+            v = rng.standard_normal(shape) * ((0.5 if name == "weight_g" else 1.0) / np.sqrt(max(1, int(np.prod(shape[1:])))))
+            if name == "weight_g":
+                v = 0.15 + 0.15 * rng.random_sample(shape)
+        elif fill_all and t.is_floating_point() and t.dim() == 1 and name == "weight":  # BatchNorm2d gain
+            v = 0.5 + rng.random_sample(shape)
+        elif fill_all and t.is_floating_point() and t.dim() == 1 and name == "bias":
             v = 0.1 * rng.standard_normal(shape)
         else:
             out[key] = t
