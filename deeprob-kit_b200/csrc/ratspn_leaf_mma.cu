@@ -73,6 +73,8 @@ struct LeafMmaArgs {
   int gen;                    // general Gaussian: x^2 images go to the global scratch too (K blocks KBn/2 .. KBn-1)
   int64_t lda;                // row stride of x (elements); columns >= D read as 0
   int nC, kchunk;             // split-K: nC chunks of kchunk K blocks (nC == 1: the whole K range per unit)
+  const float* amax_a;        // optional device scalars: max |A|, max |B| of operands that were scaled into the fp16 range by
+  const float* amax_b;        //   pow2_scale(amax) when their images were built; the result is multiplied by 1 / (sa * sb)
   float* sqsum;               // CONV launch of a unit-scale Gaussian: [Bp] -1/2 sum_f x_f^2 per sample (else NULL)
   float ascale, oscale;       // PREP multiplies the A operand by ascale; linear == 2 multiplies the result by oscale
   int linear, relu;           // linear == 2: out (B, Ntot) += result (atomic, split-K partial sums); linear != 0: generic layer, out (B, Ntot) row-major = act(x W^T + bias), cstm = bias
@@ -80,6 +82,7 @@ struct LeafMmaArgs {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int64_t ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -160,6 +163,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// power of two that brings a tensor with the given max |v| into (2^12, 2^13]: exact scaling, hi/lo fp16 stay normal over
+// the largest possible range of magnitudes below the maximum (0 / non-finite maxima: no scaling)
+__device__ __forceinline__ float pow2_scale(float amax) {
+  if (!(amax > 0.f) || !(amax <= FLT_MAX)) return 1.f;
+  int e;
+  frexpf(amax, &e);                 // amax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 13 - e);
+}
 
 constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units behind the scheduler (3 stages + 2)
 
@@ -563,6 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
     // 2 vector LDS per 4 columns + {LDS, 2 FADD, pointer add, STG} per column.
     const int et = threadIdx.x - kEpiThread0;   // 0..255
     const int ew = warp - 10;
+    const float osc = a.amax_a ? a.oscale / (pow2_scale(__ldg(a.amax_a)) * (a.amax_b ? pow2_scale(__ldg(a.amax_b)) : 1.f)) : a.oscale;
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
     const int chalf = ew >> 2;                  // which 128 columns of the tile
     float* sqw = sqw_s + ew * (16 * 32);
@@ -642,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
               float* op = a.out + (size_t)b * a.Ntot + col_base + col0;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < nvalid) atomicAdd(op + i, __uint_as_float(v[i]) * a.oscale);
+                if (i < nvalid) atomicAdd(op + i, __uint_as_float(v[i]) * osc);
             }
           } else if (a.linear) {
             // generic layer: row-major output, this thread owns 32 consecutive columns of its row
@@ -651,7 +664,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
               float r[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                r[i] = __uint_as_float(v[i]) + cst_s[col0 + i];
+                r[i] = fmaf(__uint_as_float(v[i]), osc, cst_s[col0 + i]);
                 if (a.relu) r[i] = fmaxf(r[i], 0.f);
               }
               if (nvalid == 32 && (a.Ntot & 3) == 0) {
@@ -808,6 +821,79 @@ __global__ void linear_prep_weight_kernel(const float* __restrict__ w, int N, in
   }
 }
 
+
+// ---- backward of the generic linear layer --------------------------------------------------------------
+// Operand images built directly from fp32 matrices (no PREP launch): logical matrix M (rows x kdim),
+//   M[r][k] = (TRANS ? src[k * ld + r] : src[r * ld + k]) * [msk > 0] * pow2_scale(*amax)
+// written as [ceil(rows / 256)][KBn = ceil(kdim / 32)][hi | lo][256 rows x 32 fp16, 64B-swizzled, K-major]; the rows /
+// columns past the matrix are zero.  `msk` (optional, same indexing as src) is the ReLU output whose sign gates dY.
+// Block = 32 x 8 threads, one 32 x 32 tile through shared memory so that the global reads run along the contiguous
+// dimension of src in both orientations.
+template <bool TRANS>
+__global__ void build_images_kernel(const float* __restrict__ src, const float* __restrict__ msk, int64_t rows, int64_t kdim,
+                                    int64_t ld, const float* __restrict__ amax, unsigned char* __restrict__ img, int KBn) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int kb = blockIdx.y;
+  const int64_t k0 = (int64_t)kb * 32;
+  const float scale = amax ? pow2_scale(__ldg(amax)) : 1.f;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t r = TRANS ? r0 + tx : r0 + ty + 8 * j;
+    const int64_t k = TRANS ? k0 + ty + 8 * j : k0 + tx;
+    float v = 0.f;
+    if (r < rows && k < kdim) {
+      const size_t idx = TRANS ? (size_t)k * ld + r : (size_t)r * ld + k;
+      v = src[idx];
+      if (msk && !(msk[idx] > 0.f)) v = 0.f;
+    }
+    if (TRANS) tile[tx][ty + 8 * j] = v * scale;
+    else tile[ty + 8 * j][tx] = v * scale;
+  }
+  __syncthreads();
+  const int t = ty * 32 + tx;
+  const int rr = t >> 3, c8 = t & 7;                 // row of the tile, 4-value column group
+  const float4 v = make_float4(tile[rr][4 * c8], tile[rr][4 * c8 + 1], tile[rr][4 * c8 + 2], tile[rr][4 * c8 + 3]);
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  uint2 hv, lv;
+  hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+  lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+  const int64_t r = r0 + rr;
+  unsigned char* dst = img + ((size_t)(r / kMmaTileM) * KBn + kb) * (2 * kImg);
+  const uint32_t off = sw64_off((uint32_t)(r % kMmaTileM), (uint32_t)c8 >> 1) + (c8 & 1) * 8;
+  *reinterpret_cast<uint2*>(dst + off) = hv;
+  *reinterpret_cast<uint2*>(dst + kImg + off) = lv;
+}
+
+// slots[0] = max |dy * [y > 0]|, slots[1] = max |x|, slots[2] = max |w| (as ordered uint bits of non-negative floats);
+// db[n] += sum_b dy[b, n] * [y > 0]
+__global__ void linear_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t B, int N,
+                                        float* __restrict__ db, unsigned int* __restrict__ amax_dy) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t rows_per = ceil_div_dev(B, (int64_t)gridDim.y);
+  const int64_t b0 = (int64_t)blockIdx.y * rows_per, b1 = min(B, b0 + rows_per);
+  float s = 0.f, m = 0.f;
+  if (n < N)
+    for (int64_t b = b0; b < b1; ++b) {
+      float v = dy[(size_t)b * N + n];
+      if (y && !(y[(size_t)b * N + n] > 0.f)) v = 0.f;
+      s += v;
+      m = fmaxf(m, fabsf(v));
+    }
+  if (n < N && db) atomicAdd(db + n, s);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_dy, __float_as_uint(m));
+}
+__global__ void amax_kernel(const float* __restrict__ v, int64_t n, unsigned int* __restrict__ slot) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(v[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+
 // rows of flagged 32-row groups (non-finite or huge inputs / weights), evaluated exactly in fp32 like F.linear
 __global__ void linear_exact_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                          const float* __restrict__ bias, const int* __restrict__ redo, int64_t B, int K,
@@ -953,7 +1039,7 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   DPK_CUDA_TRY(cudaMemsetAsync(a.redo, 0, mma_call_flag_ints(p) * 4, st));
   a.xlimit = (a.quad || a.gen) ? 128.f : 60000.f;   // x^2 and x must stay inside the fp16 range
   a.linear = 0; a.relu = 0; a.nC = 1; a.kchunk = a.KBn; a.ascale = 1.f; a.oscale = 1.f; a.lda = a.D;
-  a.sqsum = nullptr;
+  a.sqsum = nullptr; a.amax_a = nullptr; a.amax_b = nullptr;
   const bool want_stats = env_int("DPK_MMA_STATS", 0) != 0;
   a.stats = want_stats ? reinterpret_cast<unsigned long long*>(a.redo + p.Bp / 32 + 4) : nullptr;
   if (want_stats) DPK_CUDA_TRY(cudaMemsetAsync(a.stats, 0, 32 * 8, st));
@@ -1047,7 +1133,7 @@ int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const 
   a.redo = flg; a.unit_counter = flg + n_redo; a.wflag = wflag;
   // P = posterior * grad_out: 2^14 keeps posteriors in [0, 1] inside the fp16 range and drops the subnormal floor
   a.ascale = 16384.f; a.oscale = 1.f / 16384.f; a.xlimit = 60000.f;
-  a.linear = 2; a.relu = 0; a.stats = nullptr; a.sqsum = nullptr;
+  a.linear = 2; a.relu = 0; a.stats = nullptr; a.sqsum = nullptr; a.amax_a = nullptr; a.amax_b = nullptr;
   a.kchunk = 64; a.nC = (int)ceil_div(KBn, a.kchunk);   // <= 384 accumulations per accumulator: 2e-5 relative
   const int cap = sm_count();
   const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
@@ -1119,7 +1205,7 @@ extern "C" int dpk_linear_forward(const float* x, const float* weight, const flo
   a.wimg = ws + p.off_wimg; a.simg = nullptr; a.aimg = ws + p.off_aimg;
   a.cstm = bias; a.sq = nullptr; a.out = out;
   a.redo = flg; a.unit_counter = flg + p.Bp / 32; a.wflag = flg + p.Bp / 32 + 3;
-  a.xlimit = 60000.f; a.linear = 1; a.relu = relu ? 1 : 0; a.stats = nullptr; a.sqsum = nullptr;
+  a.xlimit = 60000.f; a.linear = 1; a.relu = relu ? 1 : 0; a.stats = nullptr; a.sqsum = nullptr; a.amax_a = nullptr; a.amax_b = nullptr;
   a.nC = 1; a.kchunk = a.KBn; a.ascale = 1.f; a.oscale = 1.f; a.lda = a.D;
   if (!(flags & DPK_F_TABLES_VALID)) {
     ProfScope prof(CAT_PREP, st, 1);
@@ -1153,6 +1239,117 @@ extern "C" int dpk_linear_forward(const float* x, const float* weight, const flo
     linear_exact_rows_kernel<<<(unsigned)(p.Bp / 32), 256, 0, st>>>(x, weight, bias, flg, p.B, in_features, out_features,
                                                                       relu ? 1 : 0, out);
     DPK_LAUNCH_CHECK("linear_exact_rows_kernel");
+  }
+  return DPK_OK;
+}
+
+// ---- dpk_linear_backward --------------------------------------------------------------------------------
+namespace dpk {
+namespace {
+struct LinearBwdPlan {
+  int64_t B, Bp;
+  int K, N;
+  int kb_n, kb_b;                 // K blocks along N (dgrad contraction) and along the batch (wgrad contraction)
+  size_t off_a_d, off_b_d, off_a_w, off_b_w, off_flags, total;   // bytes
+};
+LinearBwdPlan linear_bwd_plan(int64_t batch, int K, int N) {
+  LinearBwdPlan p;
+  p.B = batch; p.Bp = round_up(batch > 0 ? batch : 1, 256);
+  p.K = K; p.N = N;
+  p.kb_n = (int)ceil_div(N, kMmaKB); p.kb_b = (int)(p.Bp / kMmaKB);
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (off + n + 255) / 256 * 256; return o; };
+  p.off_a_d = take((size_t)ceil_div(p.Bp, kMmaTileM) * p.kb_n * 2 * kImg);      // dY            (B x N)
+  p.off_b_d = take((size_t)ceil_div(K, kMmaTileN) * p.kb_n * 2 * kImg);         // W^T           (K x N)
+  p.off_a_w = take((size_t)ceil_div(N, kMmaTileM) * p.kb_b * 2 * kImg);         // dY^T          (N x B)
+  p.off_b_w = take((size_t)ceil_div(K, kMmaTileN) * p.kb_b * 2 * kImg);         // x^T           (K x B)
+  p.off_flags = take(64 * 4);
+  p.total = off;
+  return p;
+}
+template <bool TRANS>
+int build_images(const float* src, const float* msk, int64_t rows, int64_t kdim, int64_t ld, const float* amax, unsigned char* img,
+                 int tile, cudaStream_t st) {
+  const int KBn = (int)ceil_div(kdim, kMmaKB);
+  dim3 grid((unsigned)(round_up(rows, tile) / 32), (unsigned)KBn);
+  build_images_kernel<TRANS><<<grid, dim3(32, 8), 0, st>>>(src, msk, rows, kdim, ld, amax, img, KBn);
+  DPK_LAUNCH_CHECK("build_images_kernel");
+  return DPK_OK;
+}
+}  // namespace
+}  // namespace dpk
+
+extern "C" size_t dpk_linear_backward_workspace_bytes(int64_t batch, int32_t in_features, int32_t out_features) {
+  if (batch < 0 || in_features <= 0 || out_features <= 0) return 0;
+  return linear_bwd_plan(batch, in_features, out_features).total;
+}
+
+// Backward of y = act(x W^T + b) (nn.Linear / MaskedLinear + optional ReLU, deeprob/flows/layers/coupling.py:45-56,
+// autoregressive.py:72-79) on the same tcgen05 GEMM:  g = dy * [y > 0];  dx = g W  (M = batch, N = in, K = out);
+// dW = g^T x  (M = out, N = in, K = batch, split-K with an atomic fp32 epilogue);  db = column sums of g.
+// Every operand is brought into the fp16 hi/lo range by an exact power-of-two scale derived from its max magnitude
+// on the device (gradients are routinely 1e-6 and smaller), undone in the epilogue.
+extern "C" int dpk_linear_backward(const float* x, const float* weight, const float* y, const float* dy, int64_t batch,
+                                   int32_t in_features, int32_t out_features, int32_t relu, float* dx, float* dw, float* db,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (batch < 0 || in_features <= 0 || out_features <= 0) return set_error(DPK_E_ARG, "linear backward: bad shape");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !dy || (relu && !y)) return set_error(DPK_E_ARG, "null pointer argument");
+  const LinearBwdPlan p = linear_bwd_plan(batch, in_features, out_features);
+  if (!workspace || ((uintptr_t)workspace & 255)) return set_error(DPK_E_WORKSPACE, "workspace must be 256-byte aligned");
+  if (workspace_bytes < p.total) return set_error(DPK_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, p.total);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = in_features, N = out_features;
+  const float* msk = relu ? y : nullptr;
+  int* flg = reinterpret_cast<int*>(ws + p.off_flags);        // [0..1] unit counters | [3] wflag (0) | [8..10] amax slots
+  unsigned int* amax = reinterpret_cast<unsigned int*>(flg + 8);
+  const float* amax_f = reinterpret_cast<const float*>(amax);
+  ProfScope prof(CAT_GEMM, st, 8);
+  DPK_CUDA_TRY(cudaMemsetAsync(flg, 0, 64 * 4, st));
+  if (db) DPK_CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)N * 4, st));
+  {
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)std::min<int64_t>(ceil_div(batch, 256), 256));
+    linear_bwd_stats_kernel<<<grid, 128, 0, st>>>(dy, msk, batch, N, db, amax + 0);
+    amax_kernel<<<(unsigned)std::min<int64_t>(ceil_div((int64_t)batch * K, 1024), 2048), 256, 0, st>>>(x, (int64_t)batch * K, amax + 1);
+    amax_kernel<<<(unsigned)std::min<int64_t>(ceil_div((int64_t)N * K, 1024), 2048), 256, 0, st>>>(weight, (int64_t)N * K, amax + 2);
+    DPK_LAUNCH_CHECK("linear_bwd_stats_kernel");
+  }
+  LeafMmaArgs a;
+  a.x = nullptr; a.lda = 0; a.D = 0; a.quad = 0; a.gen = 0; a.G0 = 0; a.K = 1; a.nS = 0; a.last_ks = 2;
+  a.mma_mode = env_int("DPK_MMA_MODE", 1);
+  a.simg = nullptr; a.cstm = nullptr; a.sq = nullptr; a.sqsum = nullptr; a.stats = nullptr;
+  a.redo = flg; a.wflag = flg + 3;
+  a.xlimit = 60000.f; a.relu = 0; a.ascale = 1.f; a.oscale = 1.f;
+  const int cap = sm_count();
+  const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc;
+  if (dx) {   // dx (B, K) = g (B, N) . W (N, K):  A = g, "weights" = W^T (K rows of N)
+    if ((rc = build_images<false>(dy, msk, batch, N, N, amax_f + 0, ws + p.off_a_d, kMmaTileM, st))) return rc;
+    if ((rc = build_images<true>(weight, nullptr, K, N, K, amax_f + 2, ws + p.off_b_d, kMmaTileN, st))) return rc;
+    a.B = batch; a.Bp = round_up(batch, 128); a.Ntot = K;
+    a.nM = (int)ceil_div(batch, kMmaTileM); a.nW = (int)ceil_div(K, kMmaTileN); a.KBn = p.kb_n;
+    a.aimg = ws + p.off_a_d; a.wimg = ws + p.off_b_d; a.out = dx;
+    a.unit_counter = flg + 0;
+    a.linear = 1; a.nC = 1; a.kchunk = a.KBn;
+    a.amax_a = amax_f + 0; a.amax_b = amax_f + 2;
+    ratspn_leaf_mma_kernel<false><<<std::min(cap, a.nM * a.nW), kThreads, smem, st>>>(a);
+    DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main> (dgrad)");
+  }
+  if (dw) {   // dW (N, K) = g^T (N, B) . x (B, K):  A = g^T, "weights" = x^T (K rows of B), contraction over the batch
+    DPK_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)N * K * 4, st));
+    if ((rc = build_images<true>(dy, msk, N, batch, N, amax_f + 0, ws + p.off_a_w, kMmaTileM, st))) return rc;
+    if ((rc = build_images<true>(x, nullptr, K, batch, K, amax_f + 1, ws + p.off_b_w, kMmaTileN, st))) return rc;
+    a.B = N; a.Bp = round_up(N, 128); a.Ntot = K;
+    a.nM = (int)ceil_div(N, kMmaTileM); a.nW = (int)ceil_div(K, kMmaTileN); a.KBn = (int)ceil_div(batch, kMmaKB);
+    a.aimg = ws + p.off_a_w; a.wimg = ws + p.off_b_w; a.out = dw;
+    a.unit_counter = flg + 0;         // the dgrad launch used slot 1 (main launches count in unit_counter[1]): reset below
+    a.linear = 2; a.kchunk = 64; a.nC = (int)ceil_div(a.KBn, a.kchunk);   // <= 384 accumulations per accumulator
+    a.amax_a = amax_f + 0; a.amax_b = amax_f + 1;
+    DPK_CUDA_TRY(cudaMemsetAsync(flg, 0, 8, st));
+    ratspn_leaf_mma_kernel<false><<<std::min(cap, a.nM * a.nW * a.nC), kThreads, smem, st>>>(a);
+    DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main> (wgrad)");
   }
   return DPK_OK;
 }

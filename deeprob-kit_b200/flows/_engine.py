@@ -272,6 +272,69 @@ def linear(x, weight, bias, relu, cache=None):
     return out
 
 
+class _LinearMMA(torch.autograd.Function):
+    """act(x @ weight.T + bias) with forward AND backward on the tcgen05 GEMM (dpk_linear_forward / dpk_linear_backward):
+    the training path of the conditioner MLPs (deeprob/flows/layers/coupling.py:45-56, autoregressive.py:72-79)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x = x.contiguous()
+        w = weight.contiguous()
+        out = linear(x, w, bias, relu, None)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes
+        from .. import _lib
+        x, w, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        batch, k = x.shape
+        n = w.shape[0]
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.empty_like(w) if need_w else None
+        db = torch.empty(n, dtype=torch.float32, device=x.device) if need_b else None
+        nbytes = _lib.lib().dpk_linear_backward_workspace_bytes(batch, k, n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dpk_linear_backward(_ptr(x), _ptr(w), _ptr(y), _ptr(dy), batch, k, n, 1 if ctx.relu else 0,
+                                                _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), ws.numel(), _stream(x.device))
+        _lib.check(rc, "dpk_linear_backward")
+        return dx, dw, db, None
+
+
+def linear_train(x, weight, bias, relu):
+    return _LinearMMA.apply(x, weight, bias, relu)
+
+
+def _mlp_train_plan(network, x):
+    """Like _mlp_plan, for a call that needs gradients (DPK_LINEAR_MMA_TRAIN=0 keeps the stock modules / cuBLAS;
+    =1 forces the tensor-core path for small batches, as the tests do)."""
+    import os
+    from torch import nn
+    from ..torch.utils import MaskedLinear
+    knob = os.environ.get("DPK_LINEAR_MMA_TRAIN", "")
+    if (not torch.is_grad_enabled() or not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32 or knob == "0"
+            or (x.shape[0] < MLP_MIN_BATCH and knob != "1")):
+        return None
+    mods = list(network)
+    plan = []
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if type(m) not in (nn.Linear, MaskedLinear) or m.in_features % 4 or m.weight.dtype != torch.float32:
+            return None
+        act = mods[i + 1] if i + 1 < len(mods) and not isinstance(mods[i + 1], nn.Linear) else None
+        relu = isinstance(act, nn.ReLU)
+        plan.append((m, relu, None if relu else act))
+        i += 1 if act is None else 2
+    return plan or None
+
+
 def _mlp_plan(network, x):
     """[(Linear, fused_relu, activation_module_or_None)] when `network` is a stack of nn.Linear / MaskedLinear layers
     with activations that the tcgen05 GEMM can evaluate for this call (inference on a large fp32 CUDA batch), else
@@ -328,7 +391,19 @@ def mlp(network, x, in_mask=None):
     training (any gradient needed), small batches and unusual layer stacks use the stock modules (cuBLAS)."""
     plan = _mlp_plan(network, x)
     if plan is None:
-        return network(x if in_mask is None else in_mask * x)
+        tplan = _mlp_train_plan(network, x)
+        if tplan is None:
+            return network(x if in_mask is None else in_mask * x)
+        # gradients needed: every layer is one autograd node whose forward and backward are tcgen05 GEMMs; the 0/1
+        # masks (conditioner input, MADE connectivity) are folded into the weights by differentiable tensor ops
+        for li, (m, relu, act) in enumerate(tplan):
+            weight = m.weight if getattr(m, "mask", None) is None else m.mask * m.weight
+            if li == 0 and in_mask is not None:
+                weight = weight * in_mask.reshape(1, -1)
+            x = linear_train(x, weight, m.bias, relu)
+            if act is not None:
+                x = act(x)
+        return x
     for li, (m, relu, act) in enumerate(plan):
         cache = m.__dict__.setdefault("_dpk_linear_cache", {})
         weight = _layer_weight(m, cache)

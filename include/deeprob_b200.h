@@ -296,6 +296,18 @@ int dpk_linear_forward(const float* x, const float* weight, const float* bias /*
                        int32_t in_features, int32_t out_features, int32_t relu, float* out, void* workspace,
                        size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* Backward of the same layer on the same GEMM (tcgen05, 3-pass hi/lo fp16 operands, fp32 accumulate):
+ *   g = dy * [y > 0] (relu != 0; y = the forward output) | dy;   dx (B, in) = g . weight;   dw (out, in) = g^T . x
+ *   (contraction over the batch: split-K with an atomic fp32 epilogue);   db (out) = column sums of g.
+ * dx / dw / db may be NULL (= not wanted); dw and db are OVERWRITTEN.  Operands are scaled into the fp16 range by exact
+ * powers of two derived on the device from their max magnitudes (gradients are routinely < 1e-6).
+ * Replaces the autograd backward of nn.Linear / MaskedLinear (+ ReLU) in deeprob/flows/layers/coupling.py:45-56 and
+ * deeprob/flows/layers/autoregressive.py:72-79. */
+size_t dpk_linear_backward_workspace_bytes(int64_t batch, int32_t in_features, int32_t out_features);
+int dpk_linear_backward(const float* x, const float* weight, const float* y, const float* dy, int64_t batch,
+                        int32_t in_features, int32_t out_features, int32_t relu, float* dx, float* dw, float* db,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

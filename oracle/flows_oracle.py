@@ -12,6 +12,11 @@ import torch.nn.functional as F
 
 _LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
 
+# When set to a list, `mlp` appends the per-sample distance of the hidden pre-activations from the ReLU kink
+# (min_j |h_j|) of every hidden layer it evaluates.  Gradients of a ReLU network are discontinuous there, so a
+# gradient comparison between two correctly rounded evaluations is only meaningful on samples that keep a margin.
+KINK_MARGINS = None
+
 
 def mlp(x, state, prefix, masked=False, activation=torch.relu):
     """nn.Sequential of Linear(+mask)/activation pairs ending in a Linear (coupling.py:45-56, autoregressive.py:58-70)."""
@@ -23,6 +28,8 @@ def mlp(x, state, prefix, masked=False, activation=torch.relu):
             w = state["%s%d.mask" % (prefix, i)] * w                 # MaskedLinear (torch/utils.py:96)
         h = F.linear(h, w, state["%s%d.bias" % (prefix, i)])
         if n != len(idx) - 1:
+            if KINK_MARGINS is not None and activation is torch.relu:
+                KINK_MARGINS.append(h.detach().abs().min(dim=1).values)
             h = activation(h)
     return h
 

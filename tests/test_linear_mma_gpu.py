@@ -6,7 +6,9 @@ sum (3e-5 at K = 3072); still far inside the 1e-4 of the north star."""
 import pytest
 import torch
 
-from conftest import rel_err
+import numpy as np
+
+from conftest import norm_err, rel_err
 from deeprob_kit_b200.flows import _engine
 
 pytestmark = pytest.mark.gpu
@@ -197,3 +199,80 @@ def test_chained_side_output_is_dropped_after_an_in_place_write():
         h.mul_(2.0)
         out, _ = c1.apply_backward(h)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("batch,k,n,relu,gscale", [(300, 64, 48, True, 1.0), (2500, 512, 1024, False, 1e-7),
+                                                   (4096, 1536, 512, True, 3e-4), (257, 36, 260, True, 1e3)])
+def test_linear_backward_matches_float64(batch, k, n, relu, gscale):
+    """dpk_linear_backward (dgrad, split-K wgrad, bias sums on the tcgen05 GEMM, power-of-two operand scaling) against
+    the float64 autograd of F.linear (+ReLU); gradients of very different magnitudes."""
+    from deeprob_kit_b200.flows._engine import linear_train
+    rng = np.random.RandomState(batch + k)
+    x = torch.from_numpy(rng.standard_normal((batch, k)).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)).cuda()
+    b = torch.from_numpy(rng.standard_normal(n).astype(np.float32) * 0.1).cuda()
+    dy = torch.from_numpy((rng.standard_normal((batch, n)) * rng.lognormal(0, 2, (batch, 1)) * gscale).astype(np.float32)).cuda()
+    with torch.enable_grad():
+        xa, wa, ba = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = linear_train(xa, wa, ba, relu)
+        y.backward(dy)
+        xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+        yr = torch.nn.functional.linear(xr, wr, br)
+        if relu:
+            yr = torch.relu(yr)
+        # the ReLU mask of the kernel is the sign of ITS forward output: mask the reference identically
+        mask = (y > 0).double() if relu else torch.ones_like(yr)
+        (torch.nn.functional.linear(xr, wr, br) * mask * dy.double()).sum().backward()
+    assert rel_err(y.detach(), yr.detach()) < 1e-4
+    for got, ref in ((xa.grad, xr.grad), (wa.grad, wr.grad), (ba.grad, br.grad)):
+        assert norm_err(got, ref) < 1e-4, (float((got.double() - ref).abs().max()), float(ref.abs().max()))
+
+
+def test_realnvp1d_training_gradients_through_the_tensor_core_mlp(monkeypatch):
+    """BASELINE config 4 structure in training mode with every conditioner GEMM (forward, dgrad, wgrad) on tcgen05:
+    the reference's training-mode log-likelihoods, and the gradients of the float64 oracle.  A ReLU network's
+    gradient jumps where a hidden pre-activation crosses zero, so the comparison weights out the samples that come
+    within 5e-5 of a kink in any hidden layer (an evaluation that differs by 1e-5 may legitimately sit on the other
+    side; the fp32 reference has the same property, only with a narrower band)."""
+    import oracle.flows_oracle as fo
+    import param_gen as pg
+    from conftest import load_golden
+    from helpers import flow_reference_state
+    monkeypatch.setenv("DPK_LINEAR_MMA_TRAIN", "1")
+    cfg = pg.FLOW_CASES["nvp1d_cifar"]
+    gold = load_golden("flows_nvp1d_cifar")
+    model, state = flow_reference_state(cfg)
+    # eval-mode batch norm keeps the samples independent (with batch statistics a kink of one sample leaks into
+    # the gradient of all others); the gradients still flow through every conditioner GEMM
+    model = model.cuda().eval()
+    x, g = pg.flow_inputs(cfg)
+    st64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in state.items()}
+    fo.KINK_MARGINS = []
+    try:
+        with torch.enable_grad():
+            ll64, _ = fo.flow1d_log_prob(x.double(), st64, "RealNVP1d", cfg["kw"], training=False)
+        margin = torch.stack(fo.KINK_MARGINS).min(0).values
+    finally:
+        fo.KINK_MARGINS = None
+    safe = (margin > 5e-5).double()
+    assert float(safe.mean()) > 0.25, "too few samples away from the ReLU kinks to compare"
+    ge = g.double() * safe
+    with torch.enable_grad():
+        (ll64 * ge).sum().backward()
+    from deeprob_kit_b200 import _lib
+    _lib.profile_read()
+    with torch.enable_grad():
+        out = model(x.cuda())
+        (out * ge.float().cuda()).sum().backward()
+    _, launches = _lib.profile_read()
+    assert launches["gemm"] >= 8 * 3 * 2, launches          # 8 couplings x 3 layers x (forward + backward)
+    assert rel_err(out.detach().cpu(), gold["ll"]) < 1e-4
+    assert rel_err(out.detach().cpu(), ll64.detach()) < 1e-4
+    gtol = 1e-4 + 4e-7 * float(out.abs().max())
+    checked = 0
+    for k, p in model.named_parameters():
+        if p.grad is None or k not in st64 or st64[k].grad is None:
+            continue
+        assert norm_err(p.grad, st64[k].grad) < 3 * gtol, k
+        checked += 1
+    assert checked >= 8 * 6
