@@ -200,6 +200,9 @@ def flow_fill_state(state, seed=0, fill_all=False):
             v = rng.standard_normal(shape) * (0.7 / np.sqrt(shape[1]))
         elif name == "bias" and "network" in key and t.dim() == 1 and "conv" not in key:
             v = 0.1 * rng.standard_normal(shape)
+        elif fill_all and "perm_matrices" in key:                                      # fixed 0/1 multi-scale permutations
+            out[key] = t
+            continue
         elif fill_all and t.is_floating_point() and t.dim() == 4:                      # conv kernels (weight_v | weight)
             v = rng.standard_normal(shape) * ((0.5 if name == "weight_g" else 1.0) / np.sqrt(max(1, int(np.prod(shape[1:])))))
             if name == "weight_g":
