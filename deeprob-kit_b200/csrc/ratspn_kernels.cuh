@@ -14,6 +14,10 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
 // outside the fast path's range, the caller's exact kernel must run)                [ratspn_leaf_mma.cu]
 int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, const float* g0, float* ws,
                               float* s1, float* s2, float* s0tot, const int** fallback, cudaStream_t st);
+// d LL / d x of the leaf level as a tcgen05 GEMM over the (region, channel) posteriors g0 = [G0*K][Bp]; accumulates
+// into gx (B, D)                                                                     [ratspn_leaf_mma.cu]
+int ratspn_run_leaf_bwd_x_mma(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, const float* g0, float* ws,
+                              float* gx, cudaStream_t st);
 // softmax / log-softmax tables of every sum level and of the root [ratspn_einsum.cu]
 int ratspn_run_prep_weights(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
 // product+sum level with the contraction on the tensor cores                      [ratspn_einsum_mma.cu]

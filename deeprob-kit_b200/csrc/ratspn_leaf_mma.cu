@@ -887,6 +887,15 @@ __global__ void linear_bwd_stats_kernel(const float* __restrict__ dy, const floa
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) atomicMax(amax_dy, __float_as_uint(m));
 }
+// max |v| over the first `cols` entries of every row of a (rows x ld) matrix
+__global__ void amax2d_kernel(const float* __restrict__ v, int64_t rows, int64_t cols, int64_t ld, unsigned int* __restrict__ slot) {
+  float m = 0.f;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y)
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x)
+      m = fmaxf(m, fabsf(v[r * ld + c]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
 __global__ void amax_kernel(const float* __restrict__ v, int64_t n, unsigned int* __restrict__ slot) {
   float m = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(v[i]));
@@ -1149,6 +1158,112 @@ int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const 
       S, d->mask, d->region_len, p.G0, p.K, p.dim, p.D, F, quad, fb, s1, s2, s0tot);
   DPK_LAUNCH_CHECK("stats_gather_kernel");
   *fallback = fb;
+  return DPK_OK;
+}
+
+// ---- d LL / d x of the leaf level as a GEMM ---------------------------------------------------------------
+// Gaussian:  d ll / d x_f = (mu - x_f) / sigma^2  =>  gx[b, f] = sum_{(g,k): f in g} P[b,(g,k)] mu / sigma^2  -  x_f sum P / sigma^2
+// Bernoulli: d ll / d x_f = logit                 =>  gx[b, f] = sum P logit
+// i.e. P (batch x G0*K) times the transposed, region-structured weight matrix [mu/sigma^2 | 1/sigma^2] (G0*K x 2D):
+// the same contraction shape as the forward leaf GEMM with the roles of features and (region, channel) swapped.
+__global__ void leaf_bx_amax_kernel(const float* __restrict__ p0, const float* __restrict__ p1, const int32_t* __restrict__ region_len,
+                                    int G0, int K, int dim, unsigned int* __restrict__ slot) {
+  float m = 0.f;
+  const int64_t total = (int64_t)G0 * K * dim;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % dim), g = (int)(idx / ((int64_t)dim * K));
+    if (d >= region_len[g]) continue;
+    const float inv2 = p1 ? 1.f / (p1[idx] * p1[idx]) : 1.f;
+    m = fmaxf(m, fmaxf(fabsf(p0[idx]) * inv2, p1 ? inv2 : 1.f));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+// weight images (zero-filled before): row n = feature f (second half: D + f), K index = g*K + k
+__global__ void leaf_bx_weight_kernel(const float* __restrict__ p0, const float* __restrict__ p1, const int32_t* __restrict__ mask,
+                                      const int32_t* __restrict__ region_len, int G0, int K, int dim, int D, int quad, int KBn,
+                                      const float* __restrict__ amax, unsigned char* __restrict__ wimg) {
+  const float scale = pow2_scale(__ldg(amax));
+  const int64_t total = (int64_t)G0 * K * dim;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % dim);
+    const int gk = (int)(idx / dim);
+    const int g = gk / K;
+    if (d >= region_len[g]) continue;
+    const int f = mask[(size_t)g * dim + d];
+    const float inv2 = p1 ? 1.f / (p1[idx] * p1[idx]) : 1.f;
+    const float w1 = p0[idx] * inv2 * scale, w2 = inv2 * scale;
+    auto put = [&](int n, float v) {
+      unsigned char* img = wimg + ((size_t)(n / kMmaTileN) * KBn + (gk >> 5)) * (2 * kImg);
+      const uint32_t off = sw64_off((uint32_t)(n & (kMmaTileN - 1)), (uint32_t)(gk & 31) >> 3) + (uint32_t)(gk & 7) * 2u;
+      const __half hi = __float2half_rn(v);
+      *reinterpret_cast<__half*>(img + off) = hi;
+      *reinterpret_cast<__half*>(img + kImg + off) = __float2half_rn(v - __half2float(hi));
+    };
+    put(f, w1);
+    if (quad) put(D + f, w2);
+  }
+}
+// gx[b, f] += tmp[b, f] - x[b, f] * tmp[b, D + f]   (marginalised / clamped inputs: no gradient)
+__global__ void leaf_bx_combine_kernel(const float* __restrict__ tmp, const float* __restrict__ x, int64_t B, int D, int quad,
+                                       float* __restrict__ gx) {
+  const int64_t total = B * D;
+  const int ncol = quad ? 2 * D : D;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / D;
+    const int f = (int)(idx - b * D);
+    const float xv = x[idx];
+    if (!(fabsf(xv) <= FLT_MAX)) continue;
+    float v = tmp[(size_t)b * ncol + f];
+    if (quad) v -= xv * tmp[(size_t)b * ncol + D + f];
+    gx[idx] += v;
+  }
+}
+
+int ratspn_run_leaf_bwd_x_mma(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, const float* g0, float* ws,
+                              float* gx, cudaStream_t st) {
+  const int quad = (p.kind == DPK_LEAF_GAUSSIAN) ? 1 : 0;
+  const int N = p.G0 * p.K, ncol = (quad ? 2 : 1) * p.D;
+  const int KBn = (int)ceil_div(N, kMmaKB);
+  unsigned char* aimg = reinterpret_cast<unsigned char*>(ws + p.off_bx_aimg);
+  unsigned char* wimg = reinterpret_cast<unsigned char*>(ws + p.off_bx_wimg);
+  float* tmp = ws + p.off_bx_tmp;
+  int* flg = reinterpret_cast<int*>(ws + p.off_bx_flags);      // [0..1] unit counters | [3] wflag | [8] amax P | [9] amax W
+  unsigned int* amax = reinterpret_cast<unsigned int*>(flg + 8);
+  const float* amax_f = reinterpret_cast<const float*>(amax);
+  DPK_CUDA_TRY(cudaMemsetAsync(flg, 0, 64 * 4, st));
+  DPK_CUDA_TRY(cudaMemsetAsync(wimg, 0, (size_t)ceil_div(ncol, kMmaTileN) * KBn * 2 * kImg, st));
+  const int64_t total = (int64_t)p.G0 * p.K * p.dim;
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), 4096);
+  amax2d_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div(p.B, 256), 64), (unsigned)std::min(N, 1024)), 256, 0, st>>>(g0, N, p.B, p.Bp, amax + 0);
+  leaf_bx_amax_kernel<<<blocks, 256, 0, st>>>(d->leaf_p0, d->leaf_p1, d->region_len, p.G0, p.K, p.dim, amax + 1);
+  leaf_bx_weight_kernel<<<blocks, 256, 0, st>>>(d->leaf_p0, d->leaf_p1, d->mask, d->region_len, p.G0, p.K, p.dim, p.D, quad, KBn,
+                                                amax_f + 1, wimg);
+  DPK_LAUNCH_CHECK("leaf_bx_weight_kernel");
+  // A = P^T: logical rows = samples, K index = (region, channel); g0 is [(g,k)][Bp] -> transposed builder
+  {
+    const int KB = (int)ceil_div(N, kMmaKB);
+    dim3 grid((unsigned)(round_up(p.B, kMmaTileM) / 32), (unsigned)KB);
+    build_images_kernel<true><<<grid, dim3(32, 8), 0, st>>>(g0, nullptr, p.B, N, p.Bp, amax_f + 0, aimg, KB);
+    DPK_LAUNCH_CHECK("build_images_kernel (P)");
+  }
+  LeafMmaArgs a;
+  a.x = nullptr; a.lda = 0; a.D = 0; a.quad = 0; a.gen = 0; a.G0 = 0; a.K = 1; a.nS = 0; a.last_ks = 2;
+  a.mma_mode = env_int("DPK_MMA_MODE", 1);
+  a.simg = nullptr; a.cstm = nullptr; a.sq = nullptr; a.sqsum = nullptr; a.stats = nullptr;
+  a.redo = flg; a.wflag = flg + 3; a.unit_counter = flg + 0;
+  a.xlimit = 60000.f; a.relu = 0; a.ascale = 1.f; a.oscale = 1.f;
+  a.B = p.B; a.Bp = round_up(p.B, 128); a.Ntot = ncol;
+  a.nM = (int)ceil_div(p.B, kMmaTileM); a.nW = (int)ceil_div(ncol, kMmaTileN); a.KBn = KBn;
+  a.aimg = aimg; a.wimg = wimg; a.out = tmp;
+  a.linear = 1; a.nC = 1; a.kchunk = a.KBn;
+  a.amax_a = amax_f + 0; a.amax_b = amax_f + 1;
+  const size_t smem = (size_t)kMmaStages * kStage + 2 * kMmaTileN * 4 + 8 * 16 * 32 * 4 + 256 + 1024;
+  DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ratspn_leaf_mma_kernel<false><<<std::min(sm_count(), a.nM * a.nW), kThreads, smem, st>>>(a);
+  DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<main> (d/dx)");
+  leaf_bx_combine_kernel<<<(unsigned)std::min<int64_t>(ceil_div(p.B * p.D, 256), 1 << 16), 256, 0, st>>>(tmp, x, p.B, p.D, quad, gx);
+  DPK_LAUNCH_CHECK("leaf_bx_combine_kernel");
   return DPK_OK;
 }
 

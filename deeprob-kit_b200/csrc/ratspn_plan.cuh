@@ -63,6 +63,7 @@ struct RatPlan {
   size_t off_wstat[DPK_MAX_LEVELS], off_rstat, off_s1, off_s2, off_snan, off_s0tot;
   int stats_mma;   // leaf moments of the backward as a tensor-core GEMM (ratspn_leaf_mma.cu)
   size_t off_stats_xt, off_stats_wimg, off_stats_aimg, off_stats_s, off_stats_flags;
+  size_t off_bx_aimg, off_bx_wimg, off_bx_tmp, off_bx_flags;   // d/dx as a GEMM (ratspn_run_leaf_bwd_x_mma), with stats_mma
   size_t stat_begin, stat_end;  // [stat_begin, stat_end) is zero-filled at the start of a backward
   size_t total_floats;
 };
@@ -243,6 +244,7 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     p->off_gact[l] = (flags & DPK_F_SAVE_ACTIVATIONS) ? take((size_t)p->act_regions[l] * p->act_ch[l] * p->Bp) : 0;
   p->stat_begin = p->stat_end = off;
   p->stats_mma = 0;
+  p->off_bx_aimg = p->off_bx_wimg = p->off_bx_tmp = p->off_bx_flags = 0;
   if (flags & DPK_F_SAVE_ACTIVATIONS) {
     for (int e = 0; e < p->n_sum; ++e) p->off_wstat[e] = take(p->w_floats[e]);
     p->off_rstat = take(p->r_floats);
@@ -266,6 +268,12 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
         p->off_stats_aimg = take((size_t)ceil_div(N, kMmaTileM) * KBn * 2 * img_floats);
         p->off_stats_s = take(N * F);
         p->off_stats_flags = take((size_t)round_up(N, 128) / 32 + 8);
+        // d/dx: P (batch x N) against [mu/sigma^2 | 1/sigma^2] (N x 2D)  (Bernoulli: logits, N x D)
+        const size_t ncol = (size_t)(quad ? 2 : 1) * p->D;
+        p->off_bx_aimg = take((size_t)ceil_div(round_up(p->B, 256), kMmaTileM) * ceil_div(N, kMmaKB) * 2 * img_floats);
+        p->off_bx_wimg = take((size_t)ceil_div(ncol, kMmaTileN) * ceil_div(N, kMmaKB) * 2 * img_floats);
+        p->off_bx_tmp = take((size_t)p->B * ncol);
+        p->off_bx_flags = take(64);
       }
     }
   }

@@ -272,3 +272,28 @@ def test_mma_leaf_statistics_nan_inputs_fall_back(monkeypatch):
     for key in ("s0", "s1", "s2"):
         if st.get(key) is not None:
             assert norm_err(st[key], ref[key]) < tol, key
+
+
+# ---- d LL / d x of the leaf level as the transposed GEMM (ratspn_run_leaf_bwd_x_mma) -----------------------------
+@pytest.mark.parametrize("name", ["gauss784", "gauss_scale", "bern784", "gauss784_nan"])
+def test_mma_input_gradient_matches_float64_oracle(name, monkeypatch):
+    """The gradient a flow with a RatSpn base needs (deeprob/flows/models/base.py:139): tensor-core path (selected
+    automatically for batches >= 8192, forced here) against the float64 oracle and the CUDA-core kernel."""
+    cfg = dict(CASES["gauss784"], optimize_scale=True, batch=520) if name == "gauss_scale" else dict(CASES[name])
+    if cfg["batch"] % 4:
+        cfg["batch"] += 4 - cfg["batch"] % 4
+    orc = oracle_for(cfg)[0].double()
+    x, g = pg.ratspn_inputs(cfg)
+    ref = orc.grads(x.double(), g.double(), clean_nan=True)["x"]
+    got = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("DPK_STATS_MMA", knob)
+        model = product_model(cfg, DEV, scale_grad=(name == "gauss_scale"))
+        with torch.enable_grad():
+            xd = x.to(DEV).requires_grad_(True)
+            out = model(xd)
+            (out * g.to(DEV)).sum().backward()
+        got[knob] = torch.nan_to_num(xd.grad.cpu())
+    tol = 1e-4 + 4e-7 * float(out.abs().max())
+    assert norm_err(got["1"], torch.nan_to_num(ref)) < 2 * tol
+    assert norm_err(got["1"], got["0"]) < 2 * tol
