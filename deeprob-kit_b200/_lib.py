@@ -142,6 +142,7 @@ SIGNATURES = {
                                                    c_vp, c_vp, ctypes.POINTER(RatSpnGrads), c_vp, c_sz, c_vp]),
     "dpk_ratspn_mpe": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "dpk_ratspn_sample": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_i64, c_vp, ctypes.c_uint64, c_vp, c_vp, c_sz, c_vp]),
+    "dpk_nll_loss": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "dpk_ratspn_leaf_forward": (ctypes.c_int, [ctypes.POINTER(RatSpnDesc), c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dpk_outer_sum_forward": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "dpk_mixture_forward": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),

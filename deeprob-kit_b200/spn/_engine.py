@@ -234,6 +234,38 @@ def ratspn_log_prob(model, x: torch.Tensor) -> torch.Tensor:
     return _RatSpnLogProb.apply((model, torch.is_grad_enabled()), x, *model._kernel_parameters())
 
 
+class _NllLoss(torch.autograd.Function):
+    """loss(ll, y) of the SPN models as one kernel (dpk_nll_loss); the gradient w.r.t. ll is produced by the same launch."""
+
+    @staticmethod
+    def forward(ctx, ll, y):
+        ll = _f32c(ll)
+        batch, classes = ll.shape
+        loss = torch.empty((), dtype=torch.float32, device=ll.device)
+        grad = torch.empty_like(ll)
+        yi = y.to(device=ll.device, dtype=torch.int64).contiguous() if y is not None else None
+        with torch.cuda.device(ll.device):
+            rc = _lib.lib().dpk_nll_loss(_ptr(ll), _ptr(yi), batch, classes, _ptr(loss), _ptr(grad),
+                                         _PTR(_lib.stream_ptr(ll.device)))
+        _lib.check(rc, "dpk_nll_loss")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def nll_loss(ll: torch.Tensor, y: Optional[torch.Tensor]) -> torch.Tensor:
+    """-mean(ll) for one output class, else the mean cross entropy of log_softmax(ll) against the labels y."""
+    if ll.is_cuda and ll.dim() == 2 and ll.shape[0] > 0 and (ll.shape[1] == 1 or y is not None):
+        return _NllLoss.apply(ll, y)
+    if ll.shape[-1] == 1 or y is None:            # host tensors (e.g. logged outputs): plain tensor ops
+        return -torch.mean(ll)
+    return torch.nn.functional.nll_loss(torch.log_softmax(ll, dim=1), y)
+
+
 def ratspn_mpe(model, x: torch.Tensor, y: Optional[torch.Tensor]) -> torch.Tensor:
     """RatSpn.mpe: forward keeping every level's log-likelihoods, then the top-down kernel (dpk_ratspn_mpe)."""
     x = _check_input(x, model.in_features, "RatSpn.mpe")

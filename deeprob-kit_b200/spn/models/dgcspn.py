@@ -132,9 +132,9 @@ class DgcSpn(ProbabilisticModel):
         raise NotImplementedError("Sampling is not implemented for DGC-SPNs")
 
     def loss(self, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if self.out_classes == 1:
-            return -torch.mean(x)
-        return F.nll_loss(torch.log_softmax(x, dim=1), y)
+        """models/dgcspn.py:189-196 as one kernel (csrc/train_glue.cu)."""
+        from .._engine import nll_loss
+        return nll_loss(x, None if self.out_classes == 1 else y)
 
     def apply_constraints(self):
         if self.optimize_scale:

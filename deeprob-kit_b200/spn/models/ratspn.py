@@ -172,9 +172,8 @@ class RatSpn(ProbabilisticModel):
             return self.base_layer.mpe(inputs, group, offset)
 
     def loss(self, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if self.out_classes == 1:
-            return -torch.mean(x)
-        return F.nll_loss(torch.log_softmax(x, dim=1), y)
+        """models/ratspn.py:184-191 as one kernel (value + gradient w.r.t. the log-likelihoods, no host sync)."""
+        return _engine.nll_loss(x, None if self.out_classes == 1 else y)
 
 
 class GaussianRatSpn(RatSpn):

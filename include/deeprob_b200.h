@@ -157,6 +157,11 @@ int dpk_ratspn_mpe(const dpk_ratspn_desc* desc, const float* x, int64_t batch, c
 int dpk_ratspn_sample(const dpk_ratspn_desc* desc, int64_t n_samples, const int32_t* y, uint64_t seed, float* samples,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Loss of the SPN models (deeprob/spn/models/ratspn.py:184-191, deeprob/spn/models/dgcspn.py:189-196) as one launch:
+ * classes == 1: loss = -mean(ll);  classes > 1: loss = mean_b(logsumexp_c ll[b,:] - ll[b, y[b]])  (y: int64 labels).
+ * `loss` (1 float, device) is overwritten; `grad` (B, classes) = d loss / d ll, may be NULL. */
+int dpk_nll_loss(const float* ll, const int64_t* y, int64_t batch, int32_t classes, float* loss, float* grad, void* stream);
+
 /* Stand-alone layers with the reference layouts (used by the nn.Module layer classes). */
 /* RegionGraphLayer.forward: out (B, G0, K) */
 int dpk_ratspn_leaf_forward(const dpk_ratspn_desc* desc, const float* x, int64_t batch, float* out,

@@ -294,3 +294,40 @@ def test_cache_invalidation_and_copies():
     assert not torch.allclose(a, b)
     twin = copy.deepcopy(model)
     assert twin._ws_cache == {} and torch.equal(twin(xd), b)
+
+
+def test_em_statistics_config5_slice_4096():
+    """BASELINE config 5 model (= config 2 structure) on a 4096-row slice: E-step statistics of the
+    CUDA path (tensor-core leaf moments are selected by the batch size the bench uses; forced here) against the
+    float64 oracle, accumulated over 512-row chunks (the statistics are sums over the batch)."""
+    import os
+    cfg = dict(pg.RATSPN_CASES["gauss784"], batch=4096)
+    model = product_model(cfg, DEV, scale_grad=False)
+    orc = oracle_for(cfg)[0].double()
+    x = torch.randn(4096, 784, generator=torch.Generator().manual_seed(5))
+    prev = os.environ.get("DPK_STATS_MMA")
+    os.environ["DPK_STATS_MMA"] = "1"
+    try:
+        st = model.em_statistics(x.to(DEV))
+    finally:
+        if prev is None:
+            del os.environ["DPK_STATS_MMA"]
+        else:
+            os.environ["DPK_STATS_MMA"] = prev
+    ref = None
+    for i in range(0, 4096, 512):
+        part = orc.em_statistics(x[i:i + 512].double())
+        if ref is None:
+            ref = part
+        else:
+            for k in ("ll_sum", "root_counts", "s0", "s1", "s2"):
+                ref[k] = ref[k] + part[k]
+            ref["sum_counts"] = [a + b for a, b in zip(ref["sum_counts"], part["sum_counts"])]
+    tol = TOL + 4e-7 * float(st["ll"].abs().max())
+    assert rel_err(st["ll"].sum().cpu(), ref["ll_sum"]) < TOL
+    assert norm_err(st["root_counts"], ref["root_counts"]) < tol
+    for a, b in zip(st["sum_counts"], ref["sum_counts"]):
+        assert norm_err(a, b) < tol
+    assert norm_err(st["s0"], ref["s0"]) < tol
+    assert norm_err(st["s1"], ref["s1"]) < tol
+    assert st["s2"] is None          # frozen unit scale: no second moment (the M-step re-estimates the means only)
