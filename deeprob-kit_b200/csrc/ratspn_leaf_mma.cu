@@ -173,6 +173,7 @@ __device__ __forceinline__ float pow2_scale(float amax) {
   return ldexpf(1.f, 13 - e);
 }
 
+constexpr int kConvPrefetchTiles = 32;   // CONV launch: M tiles between the one being converted and the one prefetched into L2
 constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units behind the scheduler (3 stages + 2)
 
 // GEN (PREP launch of a general Gaussian only) is a template parameter: as a run-time branch in the conversion loop
@@ -450,12 +451,15 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         // 4 i + rsub differ from row rsub by 256 i bytes, and in the swizzle term only through the parity of i).
         const int cw = warp - 2;
         const int c8 = lane & 7, rsub = lane >> 3;
-        const bool first = (j == 0);
-        const bool sqs = first && a.sqsum != nullptr;
         const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
-        uint32_t vmask = 0;
+        // bits 0-7: row b0 + 4 i is inside the batch; bit 31: first N tile of this M tile (range check + sum of
+        // squares happen there); bit 30: and the sum of squares is wanted.  One live register instead of three
+        // (the flags were spilled to local memory otherwise: a long-scoreboard stall in every K block)
+        uint32_t vmask = (j == 0 ? 0x80000000u : 0u) | ((j == 0 && a.sqsum != nullptr) ? 0x40000000u : 0u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) vmask |= (b0 + 4 * i < a.B) ? (1u << i) : 0u;
+#define first ((vmask & 0x80000000u) != 0u)
+#define sqs ((vmask & 0x40000000u) != 0u)
         const char* xb = reinterpret_cast<const char*>(a.x) + ((size_t)b0 * a.lda + (size_t)c8 * 4) * 4;
         const size_t rstride = (size_t)a.lda * 16;     // four rows down, in bytes
         const uint32_t row0 = cw * 32 + rsub;
@@ -527,6 +531,8 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
             }
           }
         }
+#undef first
+#undef sqs
       } else {
         // copy the x images of this M tile into the A half of every stage.  Thread t moves bytes
         // [16 t + 4096 i, +16), i = 0..7, of each 32 KB stage image, handled as two groups of 4 pieces; three
@@ -611,6 +617,16 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
         for (int r = 0; r < 16; ++r) sqw[r * 32 + lane] = pre[r];
         __syncwarp();
       };
+      if constexpr (CONV) {
+        // first N tile of an M tile: pull the rows of the M tile that will be handed out ~one wave of units later into
+        // L2 (one bulk prefetch per row), so that the converting feeders of its units see L2 latency, not HBM latency
+        if (j == 0) {
+          const int64_t mp = (int64_t)m + kConvPrefetchTiles;
+          const int64_t r = mp * kMmaTileM + et;
+          if (r < a.B)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.x + r * a.lda), "r"((uint32_t)(a.D * 4) & ~15u) : "memory");
+        }
+      }
       if (quad && mine) preload(0);   // written by the PREP launch
       const long long t_w0 = a.stats ? clock64() : 0;
       mbar_wait(tfull, (uint32_t)it & 1u);
