@@ -142,27 +142,54 @@ __device__ __forceinline__ void tree_issue_pair(const WgCtx& c, const CUtensorMa
   __syncwarp();
 }
 
+// The three passes hi*hi + lo*hi + hi*lo are ONE contraction over the concatenated K axis [hi | lo | hi] x [Whi | Whi | Wlo]
+// when 3*KIN tf32 values fit one 128-byte row: ceil(3*KIN / 8) MMAs instead of 3 * ceil(KIN / 8), on 128B-swizzled
+// rows.  Used for KIN <= 8; at KIN = 10 (4 MMAs instead of 6: tensor pipe 128k -> 85k cycles per SM at config 2) the
+// 30-word row image costs more registers than the 128-register budget of a 512-thread CTA has left -- the level
+// slots spill and the kernel gets slower (0.165 -> 0.221 ms, profiles/ r2 notes) -- so wider inputs keep separate
+// hi / lo images of 64-byte rows.
+
 // stage v_right (hi/lo tf32 rows), then T = A * W^T on the tensor core; returns when T is complete
 template <int KIN, int KPF = 0>
 __device__ __forceinline__ void tree_mma(WgCtx& c, const TreeArgs& a, const float (&er)[KIN], int lvl, int part,
                                          const CUtensorMap* tmap = nullptr, int pf_sample = -1, int pf_row = 0) {
-  constexpr int NK = (KIN <= 8) ? 8 : 16;
-  uint32_t hi[NK], lo[NK];
+  constexpr bool PACK = 3 * KIN <= 24;
+  if constexpr (PACK) {
+    // word w of the row: hi_j (w = j), lo_j (w = KIN + j), hi_j again (w = 2 KIN + j), 0 beyond; built chunk by chunk
+    // (4 words live at a time: a 32-register row image spilled the level slots out of the register file)
+    auto word = [&](int w) -> uint32_t {
+      if (w >= 3 * KIN) return 0u;
+      const int j = w % KIN;
+      const uint32_t h = __float_as_uint(er[j]) & 0xffffe000u;
+      return (w / KIN == 1) ? __float_as_uint(er[j] - __uint_as_float(h)) : h;
+    };
+    constexpr int NCH = (3 * KIN + 3) / 4;     // 16-byte chunks that carry data; the K steps read 8 values = 2 chunks each
+    constexpr int NCHW = (NCH + 1) / 2 * 2;
 #pragma unroll
-  for (int j = 0; j < NK; ++j) {
-    if (j < KIN) {
-      const uint32_t h = __float_as_uint(er[j < KIN ? j : 0]) & 0xffffe000u;
-      hi[j] = h;
-      lo[j] = __float_as_uint(er[j < KIN ? j : 0] - __uint_as_float(h));
-    } else {
-      hi[j] = 0u; lo[j] = 0u;
+    for (int q = 0; q < NCHW; ++q) {
+      *reinterpret_cast<uint4*>(c.a_ptr + sw128_off((uint32_t)c.tid, (uint32_t)q)) =
+          make_uint4(word(4 * q), word(4 * q + 1), word(4 * q + 2), word(4 * q + 3));
+      asm volatile("" ::: "memory");
     }
-  }
+  } else {
+    constexpr int NK = (KIN <= 8) ? 8 : 16;
+    uint32_t hi[NK], lo[NK];
 #pragma unroll
-  for (int q = 0; q < NK / 4; ++q) {
-    const uint32_t off = sw64_off((uint32_t)c.tid, (uint32_t)q);
-    *reinterpret_cast<uint4*>(c.a_ptr + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-    *reinterpret_cast<uint4*>(c.a_ptr + kAHalf + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    for (int j = 0; j < NK; ++j) {
+      if (j < KIN) {
+        const uint32_t h = __float_as_uint(er[j < KIN ? j : 0]) & 0xffffe000u;
+        hi[j] = h;
+        lo[j] = __float_as_uint(er[j < KIN ? j : 0] - __uint_as_float(h));
+      } else {
+        hi[j] = 0u; lo[j] = 0u;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NK / 4; ++q) {
+      const uint32_t off = sw64_off((uint32_t)c.tid, (uint32_t)q);
+      *reinterpret_cast<uint4*>(c.a_ptr + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      *reinterpret_cast<uint4*>(c.a_ptr + kAHalf + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
   }
   fence_async_smem();   // generic-proxy stores -> visible to the tensor core
   fence_before();       // this thread's TMEM loads of the previous accumulator are ordered before the barrier
@@ -172,16 +199,22 @@ __device__ __forceinline__ void tree_mma(WgCtx& c, const TreeArgs& a, const floa
     const uint32_t npad = a.lvl_npad[lvl];
     const uint32_t b_sm = c.w_sm + a.lvl_off[lvl] + (uint32_t)part * (2u * npad * 64u);
     const uint32_t idesc = idesc_m128(npad, 2u);
-    const uint32_t a_hi = desc_lo(c.a_sm), a_lo = a_hi + (kAHalf >> 4);
-    const uint32_t b_hi = desc_lo(b_sm), b_lo = b_hi + ((npad * 64u) >> 4);
+    const uint32_t a_hi = desc_lo(c.a_sm), b_hi = desc_lo(b_sm);
     if (elect_one()) {
-      constexpr int NKS = NK / 8;   // K steps of 8 tf32 = 32 bytes of every 64-byte row
+      if constexpr (PACK) {
+        constexpr int NKS = (3 * KIN + 7) / 8;
 #pragma unroll
-      for (int ks = 0; ks < NKS; ++ks) mma_tf32(c.d_addr, a_hi + 2 * ks, b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < NKS; ++ks) mma_tf32_sw128(c.d_addr, a_hi + 2 * ks, b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+      } else {
+        constexpr int NKS = ((KIN <= 8) ? 8 : 16) / 8;   // K steps of 8 tf32 = 32 bytes of every 64-byte row
+        const uint32_t a_lo = a_hi + (kAHalf >> 4), b_lo = b_hi + ((npad * 64u) >> 4);
 #pragma unroll
-      for (int ks = 0; ks < NKS; ++ks) mma_tf32(c.d_addr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+        for (int ks = 0; ks < NKS; ++ks) mma_tf32(c.d_addr, a_hi + 2 * ks, b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
-      for (int ks = 0; ks < NKS; ++ks) mma_tf32(c.d_addr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+        for (int ks = 0; ks < NKS; ++ks) mma_tf32(c.d_addr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) mma_tf32(c.d_addr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+      }
       commit(c.dfull);
     }
     __syncwarp();
@@ -390,7 +423,7 @@ __global__ void __launch_bounds__((KL * O > 128 || O * O > 128) ? 256 : 512, 1) 
 
 // weight images of one level: row n = o*Kin + i, column j: softmax weight W[p, o, i*Kin + j] as tf32 hi / lo
 __global__ void ratspn_prep_tree_kernel(const float* __restrict__ wsoft, int P_total, int parts, int Kin, int Nout, int OC,
-                                        int nOc, int npad, uint32_t lvl_off, uint32_t rep_bytes,
+                                        int nOc, int npad, uint32_t lvl_off, uint32_t rep_bytes, int pack,
                                         unsigned char* __restrict__ wimg) {
   const int64_t total = (int64_t)P_total * npad * 16;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -404,6 +437,19 @@ __global__ void ratspn_prep_tree_kernel(const float* __restrict__ wsoft, int P_t
     const uint32_t h = __float_as_uint(w) & 0xffffe000u;
     const float lo = w - __uint_as_float(h);
     unsigned char* img = wimg + (size_t)r * rep_bytes + lvl_off + (size_t)q * (2u * npad * 64u);
+    if (pack) {
+      // one 128-byte row [Whi (Kin) | Whi (Kin) | Wlo (Kin) | 0]: the thread of column j writes its three copies and,
+      // for the columns past 3*Kin, the zero padding
+      auto put = [&](int col, uint32_t bits) {
+        *reinterpret_cast<uint32_t*>(img + sw128_off((uint32_t)n, (uint32_t)col >> 2) + (uint32_t)(col & 3) * 4u) = bits;
+      };
+      if (j < Kin) {
+        put(j, h); put(Kin + j, h); put(2 * Kin + j, __float_as_uint(lo));
+      }
+      if (3 * Kin + j < 32) put(3 * Kin + j, 0u);
+      if (3 * Kin + 16 + j < 32) put(3 * Kin + 16 + j, 0u);
+      continue;
+    }
     const uint32_t off = sw64_off((uint32_t)n, (uint32_t)j >> 2) + (uint32_t)(j & 3) * 4u;
     *reinterpret_cast<uint32_t*>(img + off) = h;
     *reinterpret_cast<uint32_t*>(img + (size_t)npad * 64u + off) = __float_as_uint(lo);
@@ -462,7 +508,8 @@ int ratspn_run_prep_tree(const RatPlan& p, float* ws, cudaStream_t st) {
     const Chunking& ch = root ? p.cc : p.oc;
     const int64_t total = (int64_t)p.R * parts * p.tree_npad[lvl] * 16;
     ratspn_prep_tree_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 2048), 256, 0, st>>>(
-        src, p.R * parts, parts, Kin, Nout, ch.chunk, ch.count, (int)p.tree_npad[lvl], p.tree_off[lvl], p.tree_rep_bytes, wimg);
+        src, p.R * parts, parts, Kin, Nout, ch.chunk, ch.count, (int)p.tree_npad[lvl], p.tree_off[lvl], p.tree_rep_bytes,
+        3 * Kin <= 24 ? 1 : 0, wimg);
     DPK_LAUNCH_CHECK("ratspn_prep_tree_kernel");
   }
   return DPK_OK;

@@ -71,6 +71,12 @@ __host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t c) 
 constexpr uint32_t kDescHi64 = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
 
+// 128-byte swizzle: rows 128 B apart, 8-row groups 1024 B apart; 16-byte chunk c (0..7) of row `row`
+__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t c) {
+  return row * 128u + ((c ^ (row & 7u)) << 4);
+}
+constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+
 // instruction descriptor: fp32 accumulate, K-major A and B, M = 128, N = n; formats 0 = f16, 1 = bf16, 2 = tf32
 __host__ __device__ __forceinline__ uint32_t idesc_m128(uint32_t n, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | (8u << 24);
@@ -82,6 +88,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_
                "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
                "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi64)
+               : "memory");
+}
+
+__device__ __forceinline__ void mma_tf32_sw128(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+               "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi128)
                : "memory");
 }
 
