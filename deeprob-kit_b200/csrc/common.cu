@@ -105,7 +105,7 @@ extern "C" int dpk_profile_read(double* ms, int64_t* launches, int32_t ncat) {
 namespace dpk {
 namespace tc {
 int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
-                           uint32_t box_rows, uint32_t box_cols) {
+                           uint32_t box_rows, uint32_t box_cols, int swizzle128) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -120,7 +120,8 @@ int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, ui
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return set_error(DPK_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
   return DPK_OK;

@@ -10,6 +10,8 @@ int ratspn_run_prep_leaf(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, 
 // tensor-core leaf: weight images / constants, and x -> act[0] for every clean 32-sample group (flags the rest)
 int ratspn_run_prep_leaf_mma(const dpk_ratspn_desc* d, const RatPlan& p, float* ws, cudaStream_t st);
 int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_t st);
+// narrow models (G0 * K <= 256): x streamed once through TMA                         [ratspn_leaf_stream.cu]
+int ratspn_run_leaf_stream(const RatPlan& p, const float* x, float* ws, cudaStream_t st);
 // leaf moments S0/S1/S2 of the backward as a tcgen05 GEMM over the batch; *fallback = device flag (!= 0: inputs
 // outside the fast path's range, the caller's exact kernel must run)                [ratspn_leaf_mma.cu]
 int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, const float* g0, float* ws,

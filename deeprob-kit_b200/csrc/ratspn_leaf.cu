@@ -475,9 +475,13 @@ int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, 
   a.redo = nullptr;
   if (p.leaf_mma && ((uintptr_t)x & 15) == 0) {
     // tensor-core pass first; the exact kernel below then redoes only the flagged sample groups
-    int rc = ratspn_run_leaf_mma(p, x, ws, st);
+    int rc = p.leaf_stream ? ratspn_run_leaf_stream(p, x, ws, st) : ratspn_run_leaf_mma(p, x, ws, st);
     if (rc) return rc;
     a.redo = reinterpret_cast<const int*>(ws + p.off_mflags);
+  } else if (p.leaf_mma && p.off_sqsum) {
+    // unaligned x: the exact kernel does everything, quadratic term included -- every group flagged, so that the root
+    // does not add the (stale) per-sample term again
+    DPK_CUDA_TRY(cudaMemsetAsync(ws + p.off_mflags, 0x01, (size_t)p.Bp / 32 * 4, st));
   }
   a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
   a.g = leaf_geom(p);

@@ -42,6 +42,7 @@ struct RatPlan {
   size_t leaf_smem;       // dynamic shared memory of the leaf kernel
   // tensor-core leaf (ratspn_leaf_mma.cu): 0 = not used for this call
   int leaf_mma;
+  int leaf_stream;             // narrow model: streaming leaf kernel (ratspn_leaf_stream.cu); implies leaf_mma and leaf_conv
   int leaf_conv;               // main GEMM converts the fp32 inputs itself: no PREP launch, no x images, -x^2/2 added at the root
   size_t off_sqsum;            // [Bp] -1/2 sum_f x_f^2 (leaf_conv with unit-scale Gaussian leaves), else 0
   int mma_nS, mma_nW, mma_kb;  // x^2 (region indicator) N tiles, weight N tiles, 32-feature K blocks
@@ -199,7 +200,17 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
     p->mma_nS = p->mma_nW = p->mma_kb = 0;
     p->off_wimg = p->off_simg = p->off_cstm = p->off_sq = p->off_mflags = p->off_aimg = p->off_sqsum = 0;
     // With the fused upper levels behind it the GEMM converts its inputs itself (DPK_LEAF_CONV=0: separate PREP launch)
-    p->leaf_conv = (p->leaf_mma && p->tree_mma && p->fwd_kind != DPK_LEAF_GAUSSIAN && env_int("DPK_LEAF_CONV", 1) != 0) ? 1 : 0;
+    // Narrow models (all leaf columns in one N tile, HBM bound): the streaming kernel of ratspn_leaf_stream.cu, which reads
+    // x once by TMA.  DPK_LEAF_STREAM=0 disables it, =1 forces it for any batch size (tests).
+    p->leaf_stream = 0;
+    {
+      const int sknob = env_int("DPK_LEAF_STREAM", -1);
+      if (sknob != 0 && knob != 0 && p->tree_mma && p->fwd_kind != DPK_LEAF_GAUSSIAN && p->D % 4 == 0 && p->G0 * p->K <= 256 &&
+          ((batch >= kMmaMinBatch && !wide) || sknob == 1) && mma_smem <= (size_t)max_dynamic_smem()) {
+        p->leaf_stream = 1; p->leaf_mma = 1;
+      }
+    }
+    p->leaf_conv = (p->leaf_mma && p->tree_mma && p->fwd_kind != DPK_LEAF_GAUSSIAN && (env_int("DPK_LEAF_CONV", 1) != 0 || p->leaf_stream)) ? 1 : 0;
     if (p->leaf_mma) {
       p->mma_nS = (p->fwd_kind == kLeafGaussUnit && !p->leaf_conv) ? (int)ceil_div(p->G0, kMmaTileN) : 0;
       p->mma_nW = (int)ceil_div((int64_t)p->G0 * p->K, kMmaTileN);

@@ -99,6 +99,15 @@ __device__ __forceinline__ void mma_tf32_sw128(uint32_t d_tmem, uint32_t a_lo, u
                : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 operands, 16 K elements per instruction), 64B-swizzled K-major images
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+               "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi64)
+               : "memory");
+}
+
 // 32 consecutive fp32 columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -146,7 +155,7 @@ __device__ __forceinline__ float log_fast(float x) { return lg2_ftz(x) * 0.69314
 // host: encode the tensor map of a row-major 2-D fp32 tensor [rows][cols] (row stride in bytes, multiple of 16) with a
 // box of box_rows x box_cols elements, no swizzle.  Resolved through the runtime (no link-time libcuda dependency).
 int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
-                           uint32_t box_rows, uint32_t box_cols);
+                           uint32_t box_rows, uint32_t box_cols, int swizzle128 = 0);
 
 }  // namespace tc
 }  // namespace dpk

@@ -119,6 +119,7 @@ class RatSpn(ProbabilisticModel):
             self._ws_cache[key] = ws
             self._ws_sig.pop(key, None)
         sig = (ws.data_ptr(), batch, call.n_leaf, call.keep[1] is None, os.environ.get("DPK_LEAF_MMA"), os.environ.get("DPK_TREE_MMA"),
+               os.environ.get("DPK_LEAF_STREAM"),
                tuple((t.data_ptr(), t._version) for t in self._kernel_parameters()))
         valid = self.cache_tables and os.environ.get("DPK_TABLE_CACHE", "1") != "0" and self._ws_sig.get(key) == sig
         self._ws_sig[key] = sig
