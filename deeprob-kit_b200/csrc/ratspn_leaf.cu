@@ -164,14 +164,7 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
   constexpr int KH = KC / 2;
   constexpr bool QUAD = (KIND != DPK_LEAF_BERNOULLI);   // quadratic (Gaussian) vs linear (Bernoulli) term
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b0 = (int64_t)blockIdx.x * TB;
   const int CH = a.g.CH, NCH = a.g.NCH, CHP = a.g.CHP, CF = a.g.CF, NST = a.g.NST;
-  if (a.redo) {   // clean-up pass behind the tensor-core kernel: most tiles have nothing to redo
-    int any = 0;
-#pragma unroll
-    for (int s = 0; s < ST; ++s) any |= __ldg(a.redo + (b0 >> 5) + s);
-    if (!any) return;
-  }
 
   float* xs = reinterpret_cast<float*>(smem_raw);
   float* ring = xs + (size_t)a.D * TB + (size_t)warp * NST * CF;
@@ -189,10 +182,25 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  int p_stage = 0, c_stage = 0;          // ring cursors: a tile consumes exactly what it issued, so they carry over
+  uint32_t c_parity = 0;
+
+  // Tiles of this CTA.  The first pass has one tile per CTA; the clean-up pass behind the tensor-core kernel
+  // (a.redo != NULL) runs one CTA per SM over all tiles and skips those without a flagged 32-sample group -- nearly all
+  // of them: a CTA per tile would cost ~10 us of launches (227 KB of shared memory each) to find nothing to do.
+  const int64_t n_tiles = (a.B + TB - 1) / TB;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int64_t b0 = tile * TB;
+  if (a.redo) {
+    int any = 0;
+#pragma unroll
+    for (int s = 0; s < ST; ++s) any |= __ldg(a.redo + (b0 >> 5) + s);
+    if (!any) continue;
+  }
 
   // producer side (lane 0 issues; every lane tracks the cursor so the state stays warp-uniform)
   const float* p_src = a.tab + (size_t)(r_begin + warp) * per_region * CF;
-  int p_left = n_reg * per_region, p_in_region = 0, p_stage = 0;
+  int p_left = n_reg * per_region, p_in_region = 0;
   const uint32_t chunk_bytes = (uint32_t)CF * 4;
   auto issue = [&]() {
     if (p_left > 0) {
@@ -223,8 +231,6 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
   // ---- sweep ------------------------------------------------------------------------------------
   const char* xs_bytes = reinterpret_cast<const char*>(xs);
   const uint32_t lane_x = (uint32_t)lane << 2;
-  int c_stage = 0;
-  uint32_t c_parity = 0;
   for (int ri = 0; ri < n_reg; ++ri) {
     const int r = r_begin + warp + 8 * ri;
     const int len_r = __ldg(a.region_len + r);   // pad slots (d >= len_r) are not swept: they contribute exactly 0
@@ -334,6 +340,8 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
         }
       }
     }
+  }
+  __syncthreads();   // the x tile is refilled by the next iteration
   }
 }
 
@@ -493,7 +501,7 @@ int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, 
   int rsplit = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(2 * nsm, ntiles)), ceil_div(p.G0, 8));
   a.regions_per_cta = (int)round_up(ceil_div(p.G0, rsplit), 8);
   rsplit = (int)ceil_div(p.G0, a.regions_per_cta);
-  L.grid = dim3((unsigned)ntiles, (unsigned)rsplit);
+  L.grid = dim3((unsigned)((a.redo && L.mode != 0) ? std::min<int64_t>(ntiles, nsm) : ntiles), (unsigned)rsplit);
   L.smem = p.leaf_smem;
   if (p.fwd_kind == DPK_LEAF_GAUSSIAN) return launch_leaf_kind<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, L, st);
   if (p.fwd_kind == kLeafGaussUnit) return launch_leaf_kind<kLeafGaussUnit>(p.kc.chunk, a, L, st);

@@ -47,6 +47,9 @@ struct TreeArgs {
   const float* act0;            // [G0*KL][Bp]
   const unsigned char* wimg;    // [R][rep_bytes]
   float* part;                  // [R][C][Bp]
+  float* out;                   // (B, C): written here when R == 1 (nothing to combine over repetitions), else NULL
+  const float* sqsum;           // see tree_root_combine_kernel
+  const int* redo;
   const float* wlog[kTreeMaxD]; // log-softmax tables of the sum levels (exact path), [P][nOc][Kin2][OC]
   const float* rlog;            // [R][nCc][Kin2][CC]
   int64_t B, Bp;
@@ -411,6 +414,10 @@ __global__ void __launch_bounds__((KL * O > 128 || O * O > 128) ? 256 : 512, 1) 
       }
     }
     if (bad && b < a.B) tree_exact_rep(a, r, b);
+    if (a.out != nullptr && b < a.B) {   // one repetition: the root value is the result
+      const float add = (a.sqsum != nullptr && a.redo[b >> 5] == 0) ? a.sqsum[b] : 0.f;
+      for (int cls = 0; cls < a.C; ++cls) a.out[(size_t)b * a.C + cls] = a.part[(size_t)cls * a.Bp + b] + add;
+    }
   }
 
   fence_before();
@@ -520,6 +527,10 @@ int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
   a.act0 = ws + p.off_act[0];
   a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_timg);
   a.part = ws + p.off_rtmp;
+  const bool fold = p.R == 1 && env_int("DPK_TREE_FOLD", 1) != 0;
+  a.out = fold ? out : nullptr;
+  a.sqsum = p.off_sqsum ? ws + p.off_sqsum : nullptr;
+  a.redo = reinterpret_cast<const int*>(ws + p.off_mflags);
   for (int e = 0; e < kTreeMaxD; ++e) a.wlog[e] = (e < p.n_sum) ? ws + p.off_wlog[e] : nullptr;
   a.rlog = ws + p.off_rlog;
   a.B = p.B; a.Bp = p.Bp;
@@ -548,6 +559,7 @@ int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
     else return set_error(DPK_E_ARG, "tree kernel not instantiated for K=%d O=%d", p.K, p.O);
   }
   if (rc) return rc;
+  if (fold) return DPK_OK;
   ProfScope prof(CAT_ROOT, st);
   tree_root_combine_kernel<<<(unsigned)ceil_div(p.B, 256), 256, 0, st>>>(
       ws + p.off_rtmp, out, p.R, p.C, p.B, p.Bp, p.off_sqsum ? ws + p.off_sqsum : nullptr,

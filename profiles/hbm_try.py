@@ -24,12 +24,12 @@ def leaf_ms(tag):
     print('RES', tag, {k: round(v / 20, 4) for k, v in ms.items() if v > 0})
 
 
-for env in ({}, {"DPK_STREAM_DBG": "3"}, {"DPK_STREAM_DBG": "8"}, {"DPK_STREAM_SPLIT": "0"}, {"DPK_STREAM_MT": "128"},
-            {"DPK_STREAM_MT": "96"}, {"DPK_STREAM_MT": "64"}, {"DPK_STREAM_STAGES": "3"}):
+for env in ({}, {"DPK_STREAM_DBG": "3"}, {"DPK_STREAM_DBG": "8"}, {"DPK_STREAM_MT": "128"}):
     os.environ.update(env)
     leaf_ms(str(env))
     for k in env:
         del os.environ[k]
+print("stream on", json.dumps(bench.bench_hbm_bound(dev, 65536, 50)))
 os.environ["DPK_LEAF_STREAM"] = "0"
 print("stream off", json.dumps(bench.bench_hbm_bound(dev, 65536, 50)))
 del os.environ["DPK_LEAF_STREAM"]
