@@ -167,6 +167,7 @@ SIGNATURES = {
     "dpk_normal_prior_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "dpk_dgc_root_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dpk_dgc_prodsum_forward": (ctypes.c_int, [ctypes.POINTER(DgcProductDesc), c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "dpk_dgc_prodsum_backward": (ctypes.c_int, [ctypes.POINTER(DgcProductDesc), c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dpk_linear_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32]),
     "dpk_linear_backward_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32]),
     "dpk_linear_backward": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -207,6 +207,64 @@ __global__ void dgc_product_bwd_depthwise_kernel(const float* __restrict__ g, fl
   }
 }
 
+
+// Depthwise product, forward and backward, pixel-stationary: thread = destination pixel, its (up to) four source offsets
+// are computed once -- the plane-per-CTA kernels above spend their time on two integer divisions and four bounds tests
+// per element and reach a tenth of the HBM rate -- and the planes (b, c) of a slice stream through, four at a time.
+//   BWD = false: out[plane][q] = sum_tap x[plane][y(q,tap), x(q,tap)]        (src = product input,  dst = its output)
+//   BWD = true:  gx[plane][p]  = sum_tap g[plane][oh(p,tap), ow(p,tap)]       (src = output gradient, dst = input gradient)
+template <bool BWD>
+__global__ void __launch_bounds__(128) dgc_product_px_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int64_t planes, int64_t per_slice, ProdDesc d) {
+  const int n_dst = BWD ? d.H * d.W : d.OH * d.OW;
+  const int n_src = BWD ? d.OH * d.OW : d.H * d.W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_dst) return;
+  int off[4];
+  if (BWD) {
+    const int y = p / d.W, xx = p - y * d.W;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int ny = y + d.pad_top - (tap >> 1) * d.dh, nx = xx + d.pad_left - (tap & 1) * d.dw;
+      off[tap] = -1;
+      if (ny >= 0 && nx >= 0 && ny % d.sh == 0 && nx % d.sw == 0) {
+        const int oh = ny / d.sh, ow = nx / d.sw;
+        if (oh < d.OH && ow < d.OW) off[tap] = oh * d.OW + ow;
+      }
+    }
+  } else {
+    const int oh = p / d.OW, ow = p - oh * d.OW;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int y = oh * d.sh + (tap >> 1) * d.dh - d.pad_top, xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
+      off[tap] = (y >= 0 && y < d.H && xx >= 0 && xx < d.W) ? y * d.W + xx : -1;
+    }
+  }
+  const int64_t p0 = blockIdx.y * per_slice, p1 = min((long long)planes, (long long)(p0 + per_slice));
+  const float* sp = src + p0 * n_src;
+  float* dp = dst + p0 * n_dst + p;
+  int64_t pl = p0;
+  for (; pl + 4 <= p1; pl += 4) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) v[u][tap] = off[tap] >= 0 ? __ldg(sp + (size_t)u * n_src + off[tap]) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) __stcs(dp + (size_t)u * n_dst, (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]));
+    sp += (size_t)4 * n_src;
+    dp += (size_t)4 * n_dst;
+  }
+  for (; pl < p1; ++pl) {
+    float a = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) a += off[tap] >= 0 ? __ldg(sp + off[tap]) : 0.f;
+    *dp = a;
+    sp += n_src;
+    dp += n_dst;
+  }
+}
+
 __global__ void dgc_product_bwd_scatter_kernel(const float* __restrict__ g, float* __restrict__ gx, int64_t B, ProdDesc d) {
   const int OHW = d.OH * d.OW;
   for (int64_t plane = blockIdx.x; plane < B * d.OC; plane += gridDim.x) {
@@ -667,6 +725,104 @@ __global__ void __launch_bounds__(128) dgc_sum_bwd_kernel(const float* __restric
   }
 }
 
+
+// Same contract, for layers whose channels fit one register block (O <= OC, I <= IC -- every layer of the benchmark
+// configurations).  The posterior factorises, w[o,i] * exp(x_i - y_o) = w[o,i] * exp(x_i - m) * exp(m - y_o) with
+// m = max_i x_i: OC + IC exps per (pixel, sample) instead of OC * IC (the MUFU pipe bounded the kernel above), and the
+// loads of sample b + 1 are issued before the arithmetic of sample b.
+// GATHER: x is the INPUT of the depthwise product layer in front of the sum layer (d describes it) and the product value is
+// recomputed from its four taps -- the training form of the forward fusion never stores the product output.
+template <int OC, int IC, bool GATHER>
+__global__ void __launch_bounds__(128) dgc_sum_bwd_fast_kernel(const float* __restrict__ x, const float* __restrict__ wsoft,
+                                                               const float* __restrict__ y, const float* __restrict__ g,
+                                                               float* __restrict__ gx, float* __restrict__ nstat, int64_t B,
+                                                               int I, int O, int HW, int64_t per_slice, ProdDesc d) {
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hw >= HW) return;
+  int off[4] = {0, 0, 0, 0};
+  if (GATHER) {
+    const int oh = hw / d.OW, ow = hw - oh * d.OW;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int yy = oh * d.sh + (tap >> 1) * d.dh - d.pad_top, xx = ow * d.sw + (tap & 1) * d.dw - d.pad_left;
+      off[tap] = (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) ? yy * d.W + xx : -1;
+    }
+  }
+  const int HWin = GATHER ? d.H * d.W : HW;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  if (b0 >= b1) return;
+  float w[OC][IC], n[OC][IC];
+#pragma unroll
+  for (int o = 0; o < OC; ++o)
+#pragma unroll
+    for (int i = 0; i < IC; ++i) {
+      w[o][i] = (o < O && i < I) ? __ldg(wsoft + ((size_t)o * I + i) * HW + hw) : 0.f;
+      n[o][i] = 0.f;
+    }
+  const size_t sx = (size_t)I * HWin, so = (size_t)O * HW, sg = (size_t)I * HW;
+  const float* xp = x + b0 * sx + (GATHER ? 0 : hw);
+  const float* yp = y + b0 * so + hw;
+  const float* gp = g + b0 * so + hw;
+  float* gxp = gx ? gx + b0 * sg + hw : nullptr;
+  float xn[IC], yn[OC], gn[OC];
+  auto load = [&](const float* xq, const float* yq, const float* gq) {
+#pragma unroll
+    for (int i = 0; i < IC; ++i) {
+      if (GATHER) {
+        float a = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) a += off[tap] >= 0 ? __ldg(xq + (size_t)i * HWin + off[tap]) : 0.f;
+        xn[i] = (i < I) ? a : -INFINITY;
+      } else {
+        xn[i] = (i < I) ? __ldcs(xq + (size_t)i * HW) : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < OC; ++o) {
+      gn[o] = (o < O) ? __ldcs(gq + (size_t)o * HW) : 0.f;
+      yn[o] = (o < O) ? __ldcs(yq + (size_t)o * HW) : 0.f;
+    }
+  };
+  load(xp, yp, gp);
+  for (int64_t b = b0; b < b1; ++b) {
+    float xv[IC], f[OC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < IC; ++i) { xv[i] = xn[i]; m = fmaxf(m, xv[i]); }
+    if (!(fabsf(m) <= FLT_MAX)) m = 0.f;
+#pragma unroll
+    for (int o = 0; o < OC; ++o) f[o] = (gn[o] != 0.f && fabsf(yn[o]) <= FLT_MAX) ? gn[o] * __expf(fminf(m - yn[o], 80.f)) : 0.f;
+    if (b + 1 < b1) load(xp + sx, yp + so, gp + so);
+    float gi[IC];
+#pragma unroll
+    for (int i = 0; i < IC; ++i) {
+      const float e = __expf(fminf(xv[i] - m, 80.f));
+      float acc = 0.f;
+#pragma unroll
+      for (int o = 0; o < OC; ++o) {
+        const float post = w[o][i] * (e * f[o]);
+        n[o][i] += post;
+        acc += post;
+      }
+      gi[i] = acc;
+    }
+    if (gxp) {
+#pragma unroll
+      for (int i = 0; i < IC; ++i)
+        if (i < I) __stcs(gxp + (size_t)i * HW, gi[i]);
+      gxp += sg;
+    }
+    xp += sx; yp += so; gp += so;
+  }
+  if (nstat) {
+#pragma unroll
+    for (int o = 0; o < OC; ++o)
+#pragma unroll
+      for (int i = 0; i < IC; ++i)
+        if (o < O && i < I && n[o][i] != 0.f) atomicAdd(nstat + ((size_t)o * I + i) * HW + hw, n[o][i]);
+  }
+}
+
 // grad_raw[o,i,hw] += N - softmax * sum_i N
 __global__ void dgc_sum_finalize_kernel(const float* __restrict__ wsoft, const float* __restrict__ nstat,
                                         float* __restrict__ gw, int O, int I, int HW) {
@@ -865,7 +1021,14 @@ extern "C" int dpk_dgc_product_forward(const dpk_dgc_product_desc* desc, const f
     return set_error(DPK_E_ARG, "dgc_product: bad descriptor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(CAT_DGC, st);
-  dgc_product_fwd_kernel<<<plane_grid(batch * d.OC), 256, 0, st>>>(x, out, batch, d);
+  if (d.depthwise && env_int_dgc("DPK_DGC_PROD_PX", 1) != 0) {
+    const int64_t planes = batch * d.OC, bx = ceil_div((int64_t)d.OH * d.OW, 128);
+    const int64_t slices = std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)16 * sm_count(), bx), ceil_div(planes, 8)));
+    const int64_t per = ceil_div(planes, slices);
+    dgc_product_px_kernel<false><<<dim3((unsigned)bx, (unsigned)ceil_div(planes, per)), 128, 0, st>>>(x, out, planes, per, d);
+  } else {
+    dgc_product_fwd_kernel<<<plane_grid(batch * d.OC), 256, 0, st>>>(x, out, batch, d);
+  }
   DPK_LAUNCH_CHECK("dgc_product_fwd_kernel");
   return DPK_OK;
 }
@@ -879,7 +1042,14 @@ extern "C" int dpk_dgc_product_backward(const dpk_dgc_product_desc* desc, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(CAT_DGC_BWD, st, d.depthwise ? 1 : 2);
   if (d.depthwise) {
-    dgc_product_bwd_depthwise_kernel<<<plane_grid(batch * d.C), 256, 0, st>>>(grad_out, grad_x, batch, d);
+    if (env_int_dgc("DPK_DGC_PROD_PX", 1) != 0) {
+      const int64_t planes = batch * d.C, bx = ceil_div((int64_t)d.H * d.W, 128);
+      const int64_t slices = std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)16 * sm_count(), bx), ceil_div(planes, 8)));
+      const int64_t per = ceil_div(planes, slices);
+      dgc_product_px_kernel<true><<<dim3((unsigned)bx, (unsigned)ceil_div(planes, per)), 128, 0, st>>>(grad_out, grad_x, planes, per, d);
+    } else {
+      dgc_product_bwd_depthwise_kernel<<<plane_grid(batch * d.C), 256, 0, st>>>(grad_out, grad_x, batch, d);
+    }
   } else {
     DPK_CUDA_TRY(cudaMemsetAsync(grad_x, 0, (size_t)batch * d.C * d.H * d.W * sizeof(float), st));
     dgc_product_bwd_scatter_kernel<<<plane_grid(batch * d.OC), 256, 0, st>>>(grad_out, grad_x, batch, d);
@@ -1007,7 +1177,16 @@ extern "C" int dpk_dgc_sum_backward(const float* x, const float* weight, const f
   const int64_t per = slice_len(batch, bx, 16);
   dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
   float* ns = grad_weight ? nstat : nullptr;
-  if (out_channels <= 4 && in_channels <= 4)
+  const bool fast = env_int_dgc("DPK_DGC_BWD_FAST", 1) != 0;
+  if (fast && out_channels <= 8 && in_channels <= 8) {
+    // more, shorter slices than the generic kernel: 16 samples' worth of loads per thread keep HBM busy
+    const int64_t per2 = std::max<int64_t>(16, ceil_div(batch, std::max<int64_t>(1, ceil_div((int64_t)12 * sm_count(), bx))));
+    dim3 grid2((unsigned)bx, (unsigned)ceil_div(batch, per2));
+    if (out_channels <= 4 && in_channels <= 4)
+      dgc_sum_bwd_fast_kernel<4, 4, false><<<grid2, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per2, ProdDesc{});
+    else
+      dgc_sum_bwd_fast_kernel<8, 8, false><<<grid2, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per2, ProdDesc{});
+  } else if (out_channels <= 4 && in_channels <= 4)
     dgc_sum_bwd_kernel<4, 4><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per);
   else if (out_channels <= 4)
     dgc_sum_bwd_kernel<4, 8><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per);
@@ -1017,6 +1196,41 @@ extern "C" int dpk_dgc_sum_backward(const float* x, const float* weight, const f
   if (grad_weight) {
     dgc_sum_finalize_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(wsoft, nstat, grad_weight, out_channels,
                                                                               in_channels, hw);
+    DPK_LAUNCH_CHECK("dgc_sum_finalize_kernel");
+  }
+  return DPK_OK;
+}
+
+extern "C" int dpk_dgc_prodsum_backward(const dpk_dgc_product_desc* desc, const float* x, const float* weight, const float* out,
+                                        const float* grad_out, int64_t batch, int32_t out_channels, float* grad_prod,
+                                        float* grad_weight, float* scratch, void* stream) {
+  if (!desc || batch < 0 || out_channels <= 0) return set_error(DPK_E_ARG, "dgc_prodsum_bwd: bad arguments");
+  if (batch == 0) return DPK_OK;
+  if (!x || !weight || !out || !grad_out || !scratch) return set_error(DPK_E_ARG, "dgc_prodsum_bwd: null pointer");
+  const ProdDesc d = to_prod(desc);
+  const int I = d.OC, hw = d.OH * d.OW;
+  if (!d.depthwise || d.C != d.OC || I > 8 || out_channels > 8 || d.sh <= 0 || d.sw <= 0)
+    return set_error(DPK_E_ARG, "dgc_prodsum_bwd: only depthwise products with at most 8 channels in and out");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nw = (size_t)out_channels * I * hw;
+  float* wsoft = scratch;
+  float* wlog = scratch + nw;
+  float* nstat = scratch + 2 * nw;
+  ProfScope prof(CAT_DGC_BWD, st, grad_weight ? 3 : 2);
+  dgc_sum_prep_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(weight, wsoft, wlog, out_channels, I, hw);
+  DPK_LAUNCH_CHECK("dgc_sum_prep_kernel");
+  if (grad_weight) DPK_CUDA_TRY(cudaMemsetAsync(nstat, 0, nw * sizeof(float), st));
+  const int64_t bx = ceil_div(hw, 128);
+  const int64_t per = std::max<int64_t>(16, ceil_div(batch, std::max<int64_t>(1, ceil_div((int64_t)12 * sm_count(), bx))));
+  dim3 grid((unsigned)bx, (unsigned)ceil_div(batch, per));
+  float* ns = grad_weight ? nstat : nullptr;
+  if (out_channels <= 4 && I <= 4)
+    dgc_sum_bwd_fast_kernel<4, 4, true><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_prod, ns, batch, I, out_channels, hw, per, d);
+  else
+    dgc_sum_bwd_fast_kernel<8, 8, true><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_prod, ns, batch, I, out_channels, hw, per, d);
+  DPK_LAUNCH_CHECK("dgc_sum_bwd_fast_kernel<gather>");
+  if (grad_weight) {
+    dgc_sum_finalize_kernel<<<(out_channels * hw + 127) / 128, 128, 0, st>>>(wsoft, nstat, grad_weight, out_channels, I, hw);
     DPK_LAUNCH_CHECK("dgc_sum_finalize_kernel");
   }
   return DPK_OK;

@@ -2,6 +2,7 @@
 autograd node (the reference's `mpe` differentiates w.r.t. the base layer output, so the layers have
 to stay separately differentiable: deeprob/spn/models/dgcspn.py:153-184)."""
 import ctypes
+import os
 
 import torch
 
@@ -184,6 +185,58 @@ def product_mixture(x, desc, weight):
                                                 _ptr(scratch), _stream(x.device))
     _lib.check(rc, "dpk_dgc_prodsum_forward")
     return out
+
+
+class _ProductSum(torch.autograd.Function):
+    """Training form of the fusion: the forward is the same single kernel (the product output is not kept); the backward
+    recomputes the product output from the saved input (one gather pass), then runs the sum and product backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, desc):
+        out = product_mixture(x, desc, weight)
+        ctx.save_for_backward(_f32c(x), _f32c(weight), out)
+        ctx.desc = desc
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, out = ctx.saved_tensors
+        desc = ctx.desc
+        g = _f32c(g)
+        b, cout = x.shape[0], weight.shape[0]
+        hw = desc.out_height * desc.out_width
+        dev = x.device
+        gw = torch.zeros_like(weight) if ctx.needs_input_grad[1] else None
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gprod = (torch.empty(b, desc.out_channels, desc.out_height, desc.out_width, dtype=torch.float32, device=dev)
+                 if gx is not None else None)
+        scratch = torch.empty(3 * weight.numel(), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            # DPK_DGC_BWD_GATHER=1: product values recomputed inside the sum-backward kernel from the four taps (no
+            # temporary, one pass less) -- measured slower, 38.9 vs 32.8 ms at config 3: four predicated loads per value
+            if desc.out_channels <= 8 and cout <= 8 and os.environ.get("DPK_DGC_BWD_GATHER", "0") == "1":
+                rc = _lib.lib().dpk_dgc_prodsum_backward(ctypes.byref(desc), _ptr(x), _ptr(weight), _ptr(out), _ptr(g), b, cout,
+                                                         _ptr(gprod), _ptr(gw), _ptr(scratch), st)
+                _lib.check(rc, "dpk_dgc_prodsum_backward")
+            else:
+                prod = torch.empty(b, desc.out_channels, desc.out_height, desc.out_width, dtype=torch.float32, device=dev)
+                rc = _lib.lib().dpk_dgc_product_forward(ctypes.byref(desc), _ptr(x), b, _ptr(prod), st)
+                _lib.check(rc, "dpk_dgc_product_forward")
+                rc = _lib.lib().dpk_dgc_sum_backward(_ptr(prod), _ptr(weight), _ptr(out), _ptr(g), b, desc.out_channels, cout, hw,
+                                                     _ptr(gprod), _ptr(gw), _ptr(scratch), st)
+                _lib.check(rc, "dpk_dgc_sum_backward")
+                del prod
+            if gx is not None:
+                rc = _lib.lib().dpk_dgc_product_backward(ctypes.byref(desc), _ptr(gprod), b, _ptr(gx), st)
+                _lib.check(rc, "dpk_dgc_product_backward")
+        return gx, gw, None
+
+
+def product_mixture_train(x, desc, weight):
+    """product_mixture with an autograd node (see _ProductSum)."""
+    x = _check4d(x, "SpatialProductLayer.forward")
+    return _ProductSum.apply(x, weight, desc)
 
 
 def can_fuse_product_mixture(prod_layer, sum_layer) -> bool:

@@ -97,9 +97,11 @@ class DgcSpn(ProbabilisticModel):
         """Log-likelihood (B, out_classes) of x (B, C, H, W); NaN = marginalised variable."""
         h = self.base_layer(x)
         layers = list(self.layers)
-        # inference: a depthwise product layer and the sum layer behind it run as one kernel (its output, the
-        # largest tensor of the model, is never written); with gradients every layer stays its own autograd node
-        fuse = not torch.is_grad_enabled() and os.environ.get("DPK_DGC_FUSE", "1") != "0"
+        # a depthwise product layer and the sum layer behind it run as one kernel (its output, the largest tensor of
+        # the model, is never written); with gradients the pair is one autograd node that recomputes the product
+        # output in its backward (DPK_DGC_FUSE_TRAIN=0: every layer its own node)
+        grad = torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in self.parameters()))
+        fuse = os.environ.get("DPK_DGC_FUSE", "1") != "0" and (not grad or os.environ.get("DPK_DGC_FUSE_TRAIN", "1") != "0")
         i = 0
         while i < len(layers):
             layer = layers[i]
@@ -107,7 +109,10 @@ class DgcSpn(ProbabilisticModel):
             if (fuse and isinstance(layer, SpatialProductLayer) and isinstance(nxt, SpatialSumLayer)
                     and not (nxt.training and nxt.dropout is not None)
                     and _dgc_engine.can_fuse_product_mixture(layer, nxt)):
-                h = _dgc_engine.product_mixture(h, layer._desc, nxt.weight)
+                if grad:
+                    h = _dgc_engine.product_mixture_train(h, layer._desc, nxt.weight)
+                else:
+                    h = _dgc_engine.product_mixture(h, layer._desc, nxt.weight)
                 i += 2
             else:
                 h = layer(h)

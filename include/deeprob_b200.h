@@ -217,6 +217,14 @@ int dpk_dgc_sum_backward(const float* x, const float* weight, const float* out, 
 int dpk_dgc_prodsum_forward(const dpk_dgc_product_desc* desc, const float* x, const float* weight, int64_t batch,
                             int32_t out_channels, float* out, float* scratch, void* stream);
 
+/* Backward of that pair for training (autograd of dgcspn.py:224-236 + :289-304 through the fused forward, which keeps no
+ * product output): the product values are recomputed from the four taps of x (B,C,H,W); out / grad_out (B,Cout,OH,OW).
+ * grad_prod (B,C,OH,OW) or NULL = gradient w.r.t. the product OUTPUT (dpk_dgc_product_backward then gives d/dx);
+ * grad_weight (Cout,C,OH,OW) accumulated or NULL; scratch: 3*Cout*C*OH*OW floats.  C, Cout <= 8, else DPK_E_ARG. */
+int dpk_dgc_prodsum_backward(const dpk_dgc_product_desc* desc, const float* x, const float* weight, const float* out,
+                             const float* grad_out, int64_t batch, int32_t out_channels, float* grad_prod,
+                             float* grad_weight, float* scratch, void* stream);
+
 /* SpatialRootLayer.forward (dgcspn.py:343-355): x (B, Q = C*H*W), weight (classes, Q) -> out (B, classes).
  * scratch: classes*Q floats (forward), 2*classes*Q floats (backward). */
 int dpk_dgc_root_forward(const float* x, const float* weight, int64_t batch, int64_t features,

@@ -127,3 +127,32 @@ def test_shape_mismatch_raises_instead_of_reading_out_of_bounds():
     for shape in ((2, c + 1, h, w), (2, c, h + 1, w), (2, c, h, w - 1)):
         with pytest.raises(ValueError):
             model(torch.zeros(*shape, device=DEV))
+
+
+@pytest.mark.parametrize("name", ["dw8", "mnist", "mixed16"])
+def test_training_fusion_matches_layerwise(name, monkeypatch):
+    """With gradients a depthwise product + sum pair is ONE autograd node (fused forward; the backward recomputes the
+    product values from the taps, dpk_dgc_prodsum_backward, or through a temporary for more than 8 channels): values and
+    every gradient equal the layer-by-layer autograd path (DPK_DGC_FUSE_TRAIN=0), NaN inputs included."""
+    cfg = pg.DGCSPN_CASES[name]
+    x, g = pg.dgcspn_inputs(cfg)
+    x = x.clone()
+    x[::4, :, 1::3, ::2] = float("nan")
+    res = {}
+    for mode in ("1", "0", "gather"):
+        monkeypatch.setenv("DPK_DGC_FUSE_TRAIN", "0" if mode == "0" else "1")
+        monkeypatch.setenv("DPK_DGC_BWD_GATHER", "1" if mode == "gather" else "0")
+        model = dgc_product_model(cfg, DEV)
+        with torch.enable_grad():
+            xd = x.to(DEV).requires_grad_(True)
+            out = model(xd)
+            (out * g.to(DEV)).sum().backward()
+        res[mode] = (out.detach(), torch.nan_to_num(xd.grad), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    # two fp32 paths whose posteriors are exp(differences of log-values of magnitude |LL|): same bar as above
+    gtol = TOL + 4e-7 * float(res["0"][0].abs().max())
+    for mode in ("1", "gather"):
+        assert rel_err(res[mode][0], res["0"][0]) < 2e-6
+        assert norm_err(res[mode][1], res["0"][1]) < gtol
+        assert res[mode][2].keys() == res["0"][2].keys()
+        for n in res[mode][2]:
+            assert norm_err(torch.nan_to_num(res[mode][2][n]), torch.nan_to_num(res["0"][2][n])) < gtol, (mode, n)
