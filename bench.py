@@ -101,6 +101,12 @@ class ClockSampler(threading.Thread):
                 break
             time.sleep(0.004 if self.tag == "timed" else 0.02)
 
+    def mem_mhz(self):
+        try:
+            return self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_MEM) if self.ok else None
+        except Exception:  # noqa: BLE001
+            return None
+
     def summary(self, tag):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -322,6 +328,16 @@ def run_b200(args, rank, local_rank, world):
                 extras["hbm_bound_check"] = {"error": str(exc)[:300]}
     sampler.stop_flag = True
 
+    # per-rank view of the timed region (diagnostic: which rank sets the max) before the max-over-ranks
+    rank_info = [elapsed_ms / args.steps] + [prof_ms.get(k, 0.0) / prof_steps for k in ("ratspn_leaf_mma", "ratspn_einsum")]
+    mclk = sampler.mem_mhz()
+    rank_info.append(float(mclk or 0))
+    if world > 1:
+        gathered = [torch.zeros(len(rank_info), device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor(rank_info, device=dev, dtype=torch.float64))
+        per_rank = [[round(float(v), 4) for v in g] for g in gathered]
+    else:
+        per_rank = [[round(float(v), 4) for v in rank_info]]
     elapsed_ms, e2e_ms = maxr([elapsed_ms, e2e_ms])
     if "sustained_raw" in extras:
         sus_ms, n_sus = extras.pop("sustained_raw")
@@ -383,6 +399,7 @@ def run_b200(args, rank, local_rank, world):
                      "note": "the path is compute bound at this config (220 flop/B, SURVEY.md 8d): the binding roofline is "
                              "roofline_tensor; hbm_bound_check is the config where HBM binds"},
         "kernel_ms_per_step": cats,
+        "per_rank": {"columns": ["ms_per_step", "leaf_kernel_ms", "tree_kernel_ms", "mem_mhz_after"], "rows": per_rank},
         "kernel_ms_source": "separate eager pass of %d steps with CUDA events around every launch group" % prof_steps,
     }
     if mma:

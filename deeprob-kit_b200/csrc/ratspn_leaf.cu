@@ -94,7 +94,8 @@ struct LeafArgs {
   const float* tab;          // chunked table, see ratspn_plan.cuh
   const float* cd;           // [G0][nKc][dim][KC]
   const float* cst;          // [G0][Kp]
-  float* out;                // [G0][K][Bp]
+  float* out;                // [G0][K][Bp], or tile-major (out_cs, out_ts: RatPlan::act0_cs / act0_ts)
+  int64_t out_cs, out_ts;
   const int* redo;           // NULL, or [Bp/32]: only tiles with a flagged 32-sample group are computed
   int64_t B, Bp;
   int D, G0, K, dim, nKc, regions_per_cta;
@@ -336,7 +337,10 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
         const int kk = c * KC + k;
         if (kk < a.K) {
 #pragma unroll
-          for (int s = 0; s < ST; ++s) a.out[((size_t)r * a.K + kk) * a.Bp + b0 + lane + 32 * s] = val[s][k];
+          for (int s = 0; s < ST; ++s) {
+            const int64_t b = b0 + lane + 32 * s;
+            a.out[(b >> 7) * a.out_ts + ((size_t)r * a.K + kk) * a.out_cs + (b & 127)] = val[s][k];
+          }
         }
       }
     }
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(256) ratspn_leaf_wide_kernel(const LeafArgs a)
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
         const int kk = c * KC + k;
-        if (kk < a.K && b < a.Bp) a.out[((size_t)r * a.K + kk) * a.Bp + b] = val[k];
+        if (kk < a.K && b < a.Bp) a.out[(b >> 7) * a.out_ts + ((size_t)r * a.K + kk) * a.out_cs + (b & 127)] = val[k];
       }
     }
   }
@@ -492,6 +496,7 @@ int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, 
     DPK_CUDA_TRY(cudaMemsetAsync(ws + p.off_mflags, 0x01, (size_t)p.Bp / 32 * 4, st));
   }
   a.B = p.B; a.Bp = p.Bp; a.D = p.D; a.G0 = p.G0; a.K = p.K; a.dim = p.dim; a.nKc = p.kc.count;
+  a.out_cs = p.act0_cs; a.out_ts = p.act0_ts;
   a.g = leaf_geom(p);
   const int nsm = sm_count();
   LeafLaunch L;

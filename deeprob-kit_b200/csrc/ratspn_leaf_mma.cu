@@ -64,7 +64,8 @@ struct LeafMmaArgs {
   const unsigned char* simg;  // [nS][KBn][16 KB] region indicator (exact in fp16)
   const float* cstm;          // [Ntot] additive constant of every column
   float* sq;                  // [G0][Bp] scratch: -1/2 sum_{f in region} x_f^2
-  float* out;                 // [Ntot][Bp]
+  float* out;                 // [Ntot][Bp]; leaf role: element (column c, sample b) at (b >> 7) * out_ts + c * out_cs + (b & 127)
+  int64_t out_cs, out_ts;     // (Bp, 128) = column-major, (128, Ntot * 128) = tile-major (RatPlan::act0_cs / act0_ts)
   int* redo;                  // [Bp/32] groups the exact kernel must redo
   const int* wflag;           // != 0: parameters not representable, redo everything
   int* unit_counter;          // [2] dynamic scheduler of the two launches (zeroed before)
@@ -694,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
               }
             }
           } else if (nvalid == 32 && bok && !wide) {
-            float* op = a.out + (size_t)(col_base + col0) * a.Bp + b;
+            float* op = a.out + (b >> 7) * a.out_ts + (size_t)(col_base + col0) * a.out_cs + (b & 127);
             const float4* c4 = reinterpret_cast<const float4*>(cst_s + col0);
             const int4* o4 = reinterpret_cast<const int4*>(gcol_s + col0);
             if (quad) {
@@ -702,19 +703,19 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
               for (int i4 = 0; i4 < 8; ++i4) {
                 const float4 c = c4[i4];
                 const int4 o = o4[i4];
-                __stcs(op, __uint_as_float(v[4 * i4 + 0]) + (c.x + sqwl[o.x])); op += a.Bp;
-                __stcs(op, __uint_as_float(v[4 * i4 + 1]) + (c.y + sqwl[o.y])); op += a.Bp;
-                __stcs(op, __uint_as_float(v[4 * i4 + 2]) + (c.z + sqwl[o.z])); op += a.Bp;
-                __stcs(op, __uint_as_float(v[4 * i4 + 3]) + (c.w + sqwl[o.w])); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 0]) + (c.x + sqwl[o.x])); op += a.out_cs;
+                __stcs(op, __uint_as_float(v[4 * i4 + 1]) + (c.y + sqwl[o.y])); op += a.out_cs;
+                __stcs(op, __uint_as_float(v[4 * i4 + 2]) + (c.z + sqwl[o.z])); op += a.out_cs;
+                __stcs(op, __uint_as_float(v[4 * i4 + 3]) + (c.w + sqwl[o.w])); op += a.out_cs;
               }
             } else {
 #pragma unroll
               for (int i4 = 0; i4 < 8; ++i4) {
                 const float4 c = c4[i4];
-                __stcs(op, __uint_as_float(v[4 * i4 + 0]) + c.x); op += a.Bp;
-                __stcs(op, __uint_as_float(v[4 * i4 + 1]) + c.y); op += a.Bp;
-                __stcs(op, __uint_as_float(v[4 * i4 + 2]) + c.z); op += a.Bp;
-                __stcs(op, __uint_as_float(v[4 * i4 + 3]) + c.w); op += a.Bp;
+                __stcs(op, __uint_as_float(v[4 * i4 + 0]) + c.x); op += a.out_cs;
+                __stcs(op, __uint_as_float(v[4 * i4 + 1]) + c.y); op += a.out_cs;
+                __stcs(op, __uint_as_float(v[4 * i4 + 2]) + c.z); op += a.out_cs;
+                __stcs(op, __uint_as_float(v[4 * i4 + 3]) + c.w); op += a.out_cs;
               }
             }
           } else {
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
                   const int r = gcol_s[col0 + i] >> 5;
                   add += (r < 16) ? sqw[r * 32 + lane] : __ldcg(a.sq + (size_t)(g_lo + r) * a.Bp + b);
                 }
-                __stcs(a.out + (size_t)(col_base + col0 + i) * a.Bp + b, __uint_as_float(v[i]) + add);
+                __stcs(a.out + (b >> 7) * a.out_ts + (size_t)(col_base + col0 + i) * a.out_cs + (b & 127), __uint_as_float(v[i]) + add);
               }
             }
           }
@@ -1058,6 +1059,7 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
   a.cstm = ws + p.off_cstm;
   a.sq = ws + p.off_sq;
   a.out = ws + p.off_act[0];
+  a.out_cs = p.act0_cs; a.out_ts = p.act0_ts;
   a.redo = reinterpret_cast<int*>(ws + p.off_mflags);
   a.unit_counter = a.redo + p.Bp / 32;
   a.wflag = a.redo + p.Bp / 32 + 3;
@@ -1147,7 +1149,7 @@ int ratspn_run_leaf_stats_mma(const dpk_ratspn_desc* d, const RatPlan& p, const 
     DPK_LAUNCH_CHECK("linear_prep_weight_kernel (stats)");
   }
   LeafMmaArgs a;
-  a.x = g0; a.B = N; a.Bp = round_up(N, 128);
+  a.x = g0; a.B = N; a.Bp = round_up(N, 128); a.out_cs = a.Bp; a.out_ts = 128;
   a.lda = p.Bp; a.D = (p.B % 4 == 0) ? (int)p.B : (int)p.Bp;   // pad samples of P are never read when B % 4 == 0
   a.quad = 0; a.gen = 0; a.G0 = 0; a.K = 1; a.Ntot = F;
   a.nS = 0; a.nW = nW; a.KBn = KBn; a.last_ks = 2;
@@ -1269,7 +1271,7 @@ int ratspn_run_leaf_bwd_x_mma(const dpk_ratspn_desc* d, const RatPlan& p, const 
   a.simg = nullptr; a.cstm = nullptr; a.sq = nullptr; a.sqsum = nullptr; a.stats = nullptr;
   a.redo = flg; a.wflag = flg + 3; a.unit_counter = flg + 0;
   a.xlimit = 60000.f; a.relu = 0; a.ascale = 1.f; a.oscale = 1.f;
-  a.B = p.B; a.Bp = round_up(p.B, 128); a.Ntot = ncol;
+  a.B = p.B; a.Bp = round_up(p.B, 128); a.Ntot = ncol; a.out_cs = a.Bp; a.out_ts = 128;
   a.nM = (int)ceil_div(p.B, kMmaTileM); a.nW = (int)ceil_div(ncol, kMmaTileN); a.KBn = KBn;
   a.aimg = aimg; a.wimg = wimg; a.out = tmp;
   a.linear = 1; a.nC = 1; a.kchunk = a.KBn;
@@ -1327,7 +1329,7 @@ extern "C" int dpk_linear_forward(const float* x, const float* weight, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int* flg = reinterpret_cast<int*>(ws + p.off_flags);
   LeafMmaArgs a;
-  a.x = x; a.B = p.B; a.Bp = p.Bp; a.D = in_features;
+  a.x = x; a.B = p.B; a.Bp = p.Bp; a.D = in_features; a.out_cs = a.Bp; a.out_ts = 128;
   a.quad = 0; a.gen = 0; a.G0 = 0; a.K = 1; a.Ntot = out_features;
   a.nS = 0; a.nW = p.nW; a.KBn = p.KBn;
   a.last_ks = ((in_features + 15) / 16) % 2 == 1 ? 1 : 2;
@@ -1459,7 +1461,7 @@ extern "C" int dpk_linear_backward(const float* x, const float* weight, const fl
   if (dx) {   // dx (B, K) = g (B, N) . W (N, K):  A = g, "weights" = W^T (K rows of N)
     if ((rc = build_images<false>(dy, msk, batch, N, N, amax_f + 0, ws + p.off_a_d, kMmaTileM, st))) return rc;
     if ((rc = build_images<true>(weight, nullptr, K, N, K, amax_f + 2, ws + p.off_b_d, kMmaTileN, st))) return rc;
-    a.B = batch; a.Bp = round_up(batch, 128); a.Ntot = K;
+    a.B = batch; a.Bp = round_up(batch, 128); a.Ntot = K; a.out_cs = a.Bp; a.out_ts = 128;
     a.nM = (int)ceil_div(batch, kMmaTileM); a.nW = (int)ceil_div(K, kMmaTileN); a.KBn = p.kb_n;
     a.aimg = ws + p.off_a_d; a.wimg = ws + p.off_b_d; a.out = dx;
     a.unit_counter = flg + 0;
@@ -1472,7 +1474,7 @@ extern "C" int dpk_linear_backward(const float* x, const float* weight, const fl
     DPK_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)N * K * 4, st));
     if ((rc = build_images<true>(dy, msk, N, batch, N, amax_f + 0, ws + p.off_a_w, kMmaTileM, st))) return rc;
     if ((rc = build_images<true>(x, nullptr, K, batch, K, amax_f + 1, ws + p.off_b_w, kMmaTileN, st))) return rc;
-    a.B = N; a.Bp = round_up(N, 128); a.Ntot = K;
+    a.B = N; a.Bp = round_up(N, 128); a.Ntot = K; a.out_cs = a.Bp; a.out_ts = 128;
     a.nM = (int)ceil_div(N, kMmaTileM); a.nW = (int)ceil_div(K, kMmaTileN); a.KBn = (int)ceil_div(batch, kMmaKB);
     a.aimg = ws + p.off_a_w; a.wimg = ws + p.off_b_w; a.out = dw;
     a.unit_counter = flg + 0;         // the dgrad launch used slot 1 (main launches count in unit_counter[1]): reset below

@@ -49,7 +49,8 @@ constexpr uint32_t kWImg = 256 * 64;          // stride of the hi / lo weight im
 struct StreamArgs {
   const unsigned char* wimg;   // [KBn][hi | lo][256 columns x 64 B]   (N tile 0 of ratspn_run_prep_leaf_mma)
   const float* cstm;           // [Ntot]
-  float* out;                  // [Ntot][Bp]
+  float* out;                  // act[0]: element (column c, sample b) at (b >> 7) * out_ts + c * out_cs + (b & 127)
+  int64_t out_cs, out_ts;
   float* sqsum;                // [Bp] or NULL: -1/2 sum_f x_f^2
   int* redo;                   // [Bp/32]
   const int* wflag;
@@ -244,11 +245,11 @@ __global__ void __launch_bounds__(kSThreads, 1) ratspn_leaf_stream_kernel(const 
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
           }
           if (ok && !(a.dbg & 2)) {
-            float* op = a.out + (size_t)c0 * a.Bp + b;
+            float* op = a.out + (b >> 7) * a.out_ts + (size_t)c0 * a.out_cs + (b & 127);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (c0 + i < a.Ntot) __stcs(op, __uint_as_float(v[i]) + __ldg(a.cstm + c0 + i));
-              op += a.Bp;
+              op += a.out_cs;
             }
           }
         }
@@ -274,6 +275,7 @@ int ratspn_run_leaf_stream(const RatPlan& p, const float* x, float* ws, cudaStre
   a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_wimg);
   a.cstm = ws + p.off_cstm;
   a.out = ws + p.off_act[0];
+  a.out_cs = p.act0_cs; a.out_ts = p.act0_ts;
   a.sqsum = p.off_sqsum ? ws + p.off_sqsum : nullptr;
   a.redo = reinterpret_cast<int*>(ws + p.off_mflags);
   a.wflag = a.redo + p.Bp / 32 + 3;

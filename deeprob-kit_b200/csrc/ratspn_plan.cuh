@@ -42,6 +42,8 @@ struct RatPlan {
   size_t leaf_smem;       // dynamic shared memory of the leaf kernel
   // tensor-core leaf (ratspn_leaf_mma.cu): 0 = not used for this call
   int leaf_mma;
+  int act0_tiled;              // act[0] as [128-sample tile][G0*K columns][128] (fused tree kernel behind it), else [G0*K][Bp]
+  int64_t act0_cs, act0_ts;    // element (column c, sample b) of act[0]: (b >> 7) * act0_ts + c * act0_cs + (b & 127)
   int leaf_stream;             // narrow model: streaming leaf kernel (ratspn_leaf_stream.cu); implies leaf_mma and leaf_conv
   int leaf_conv;               // main GEMM converts the fp32 inputs itself: no PREP launch, no x images, -x^2/2 added at the root
   size_t off_sqsum;            // [Bp] -1/2 sum_f x_f^2 (leaf_conv with unit-scale Gaussian leaves), else 0
@@ -229,6 +231,12 @@ static inline int make_plan(const dpk_ratspn_desc* d, int64_t batch, uint32_t fl
       p->off_mflags = take((size_t)p->Bp / 32 + 4 + 64);   // redo | wflag | unit counters | debug stats
     }
   }
+  // With the tree kernel behind it act[0] is tile-major: a 128-sample tile's G0*K columns are one contiguous block, so the
+  // tree kernel's TMA box (2K columns x 128 samples) and a leaf epilogue's stores touch one page instead of 2K resp. 256
+  // pages Bp*4 bytes apart (DPK_ACT_TILED=0: column-major like the layer-wise path).
+  p->act0_tiled = (p->tree_mma && env_int("DPK_ACT_TILED", 1) != 0) ? 1 : 0;
+  p->act0_cs = p->act0_tiled ? 128 : p->Bp;
+  p->act0_ts = p->act0_tiled ? (int64_t)p->G0 * p->K * 128 : 128;
   for (int l = 0; l < p->depth; ++l) {
     p->act_regions[l] = p->G0 >> l;
     p->act_ch[l] = (l == 0) ? p->K : p->O;

@@ -44,12 +44,11 @@ constexpr uint32_t kABytes = 2 * kAHalf;         // hi | lo
 constexpr float kTinySumT = 1e-30f;
 
 struct TreeArgs {
-  const float* act0;            // [G0*KL][Bp]
+  const float* act0;            // element (column c, sample b) at (b >> 7) * act_ts + c * act_cs + (b & 127)  (RatPlan::act0_*)
+  int64_t act_cs, act_ts;
+  int tile_rows, c0_step;       // tile-major act[0]: (G0*KL, 0); column-major: (0, 128)
   const unsigned char* wimg;    // [R][rep_bytes]
   float* part;                  // [R][C][Bp]
-  float* out;                   // (B, C): written here when R == 1 (nothing to combine over repetitions), else NULL
-  const float* sqsum;           // see tree_root_combine_kernel
-  const int* redo;
   const float* wlog[kTreeMaxD]; // log-softmax tables of the sum levels (exact path), [P][nOc][Kin2][OC]
   const float* rlog;            // [R][nCc][Kin2][CC]
   int64_t B, Bp;
@@ -84,18 +83,18 @@ __device__ __noinline__ void tree_exact_rep(const TreeArgs& a, int r, int64_t b)
   float cur[16], tmp[16];
   const int n0 = 1 << (d - 1);
   for (int n = 0; n < n0; ++n) {
-    const float* lp = a.act0 + (size_t)(((r << d) + 2 * n) * KL) * a.Bp + b;
-    const float* rp = lp + (size_t)KL * a.Bp;
+    const float* lp = a.act0 + (b >> 7) * a.act_ts + (size_t)(((r << d) + 2 * n) * KL) * a.act_cs + (b & 127);
+    const float* rp = lp + (size_t)KL * a.act_cs;
     if (d == 1) {
       for (int c = 0; c < a.C; ++c)
         a.part[((size_t)r * a.C + c) * a.Bp + b] =
-            tree_exact_lse(lp, rp, a.Bp, KL, a.rlog + ((size_t)(r * a.nCc + c / a.CCc) * KL * KL) * a.CCc + c % a.CCc, a.CCc);
+            tree_exact_lse(lp, rp, a.act_cs, KL, a.rlog + ((size_t)(r * a.nCc + c / a.CCc) * KL * KL) * a.CCc + c % a.CCc, a.CCc);
       return;
     }
     {
       const int p = r * n0 + n;
       for (int o = 0; o < O; ++o)
-        cur[o] = tree_exact_lse(lp, rp, a.Bp, KL, a.wlog[0] + ((size_t)(p * a.nOc + o / a.OCc) * KL * KL) * a.OCc + o % a.OCc, a.OCc);
+        cur[o] = tree_exact_lse(lp, rp, a.act_cs, KL, a.wlog[0] + ((size_t)(p * a.nOc + o / a.OCc) * KL * KL) * a.OCc + o % a.OCc, a.OCc);
     }
     for (int L = 1; L < d; ++L) {
       const int idx = n >> (L - 1);
@@ -352,7 +351,7 @@ __global__ void __launch_bounds__((KL * O > 128 || O * O > 128) ? 256 : 512, 1) 
   const int t_first = blockIdx.y * a.G + c.wg, t_step = a.n_chunks * a.G;
   // rows of this repetition's leaf regions: region g, channel k -> row (g*KL + k), sample-minor
   const int row_base = (r << d) * KL;
-  if (c.warp_in_wg == 1 && t_first < a.n_tiles) tree_issue_pair<KL>(c, &tmap, t_first * kTile, row_base);
+  if (c.warp_in_wg == 1 && t_first < a.n_tiles) tree_issue_pair<KL>(c, &tmap, t_first * a.c0_step, t_first * a.tile_rows + row_base);
   mbar_wait(wfull, 0u);
 
 #pragma unroll 1
@@ -376,9 +375,13 @@ __global__ void __launch_bounds__((KL * O > 128 || O * O > 128) ? 256 : 512, 1) 
 #pragma unroll
       for (int k = 0; k < KL; ++k) { el[k] = exp_fast(el[k] - ml); er[k] = exp_fast(er[k] - mr); }
       // the next pair of leaf regions (of this tile, else the first pair of the warpgroup's next tile)
-      int pf_sample = -1, pf_row = row_base;
-      if (n + 1 < n0) { pf_sample = t * kTile; pf_row = row_base + 2 * (n + 1) * KL; }
-      else if (t + t_step < a.n_tiles) pf_sample = (t + t_step) * kTile;
+      // TMA coordinates of the next pair: (sample, column) of the column-major act[0], or (0, tile * G0*K + column) of the
+      // tile-major one (c0_step = 128 resp. 0, tile_rows = 0 resp. G0*K)
+      int pf_tile = -1, pf_row = row_base;
+      if (n + 1 < n0) { pf_tile = t; pf_row = row_base + 2 * (n + 1) * KL; }
+      else if (t + t_step < a.n_tiles) pf_tile = t + t_step;
+      const int pf_sample = pf_tile < 0 ? -1 : pf_tile * a.c0_step;
+      pf_row += max(pf_tile, 0) * a.tile_rows;
       if (d == 1) {
         tree_root<KL, KL>(c, a, el, er, ml + mr, r, b, &bad, &tmap, pf_sample, pf_row);
         break;
@@ -414,10 +417,6 @@ __global__ void __launch_bounds__((KL * O > 128 || O * O > 128) ? 256 : 512, 1) 
       }
     }
     if (bad && b < a.B) tree_exact_rep(a, r, b);
-    if (a.out != nullptr && b < a.B) {   // one repetition: the root value is the result
-      const float add = (a.sqsum != nullptr && a.redo[b >> 5] == 0) ? a.sqsum[b] : 0.f;
-      for (int cls = 0; cls < a.C; ++cls) a.out[(size_t)b * a.C + cls] = a.part[(size_t)cls * a.Bp + b] + add;
-    }
   }
 
   fence_before();
@@ -525,12 +524,9 @@ int ratspn_run_prep_tree(const RatPlan& p, float* ws, cudaStream_t st) {
 int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
   TreeArgs a;
   a.act0 = ws + p.off_act[0];
+  a.act_cs = p.act0_cs; a.act_ts = p.act0_ts; a.tile_rows = p.act0_tiled ? p.G0 * p.K : 0; a.c0_step = p.act0_tiled ? 0 : kTile;
   a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_timg);
   a.part = ws + p.off_rtmp;
-  const bool fold = p.R == 1 && env_int("DPK_TREE_FOLD", 1) != 0;
-  a.out = fold ? out : nullptr;
-  a.sqsum = p.off_sqsum ? ws + p.off_sqsum : nullptr;
-  a.redo = reinterpret_cast<const int*>(ws + p.off_mflags);
   for (int e = 0; e < kTreeMaxD; ++e) a.wlog[e] = (e < p.n_sum) ? ws + p.off_wlog[e] : nullptr;
   a.rlog = ws + p.off_rlog;
   a.B = p.B; a.Bp = p.Bp;
@@ -544,7 +540,8 @@ int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
   const size_t smem = 1024 + (((size_t)p.tree_rep_bytes + 1023) & ~(size_t)1023) + (size_t)a.G * (kABytes + 2u * p.K * 512u) + 128;
   // leaf activations as a 2-D tensor [G0*K rows][Bp samples]; box = one pair of sibling regions x one sample tile
   alignas(64) CUtensorMap tmap;
-  int rc = make_tensor_map_2d_f32(&tmap, a.act0, (uint64_t)p.G0 * p.K, (uint64_t)p.Bp, (uint64_t)p.Bp * 4, 2u * p.K, kTile);
+  int rc = p.act0_tiled ? make_tensor_map_2d_f32(&tmap, a.act0, (uint64_t)(p.Bp / 128) * p.G0 * p.K, 128, 512, 2u * p.K, kTile)
+                        : make_tensor_map_2d_f32(&tmap, a.act0, (uint64_t)p.G0 * p.K, (uint64_t)p.Bp, (uint64_t)p.Bp * 4, 2u * p.K, kTile);
   if (rc) return rc;
   rc = DPK_E_ARG;
   {
@@ -559,7 +556,6 @@ int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
     else return set_error(DPK_E_ARG, "tree kernel not instantiated for K=%d O=%d", p.K, p.O);
   }
   if (rc) return rc;
-  if (fold) return DPK_OK;
   ProfScope prof(CAT_ROOT, st);
   tree_root_combine_kernel<<<(unsigned)ceil_div(p.B, 256), 256, 0, st>>>(
       ws + p.off_rtmp, out, p.R, p.C, p.B, p.Bp, p.off_sqsum ? ws + p.off_sqsum : nullptr,
