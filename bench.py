@@ -384,7 +384,7 @@ def run_b200(args, rank, local_rank, world):
         "clocks": clk,
         "e2e": {"value": world * B * D / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * C * 4, "steps": e2e_steps,
-                "api": "deeprob_kit_b200.spn.streaming.log_prob_host (pinned host in/out, 2-stream chunk pipeline, "
+                "api": "deeprob_kit_b200.spn.streaming.log_prob_host (pinned host in/out, copy stream + compute stream, 3-buffer ring of 8 192-row chunks, "
                        "returns after the last D2H copy landed)"},
         "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
