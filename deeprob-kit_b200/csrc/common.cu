@@ -65,6 +65,11 @@ ProfScope::~ProfScope() {
   }
 }
 
+int pdl_mode() {
+  const char* v = getenv("DPK_PDL");      // read per call: tests and A/B runs switch it
+  return (v && *v) ? (*v == '0' ? 0 : 1) : -1;
+}
+
 int sm_count() { return attr().sms; }
 int max_dynamic_smem() { return attr().smem; }
 

@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(256, 1) ratspn_leaf_kernel(const LeafArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  pdl_launch_dependents();
+  pdl_wait();              // flags, tables and act[0] come from the launches before this one
   int p_stage = 0, c_stage = 0;          // ring cursors: a tile consumes exactly what it issued, so they carry over
   uint32_t c_parity = 0;
 
@@ -414,6 +416,7 @@ struct LeafLaunch {
   int mode;      // 2: 64-sample tile, 1: 32-sample tile, 0: wide fallback
   dim3 grid;
   size_t smem;
+  bool pdl;      // redo pass of a narrow model: staged behind the leaf launch (common.cuh)
 };
 
 template <int KC, int KIND>
@@ -422,15 +425,18 @@ static int launch_leaf_k(const LeafArgs& a, const LeafLaunch& L, cudaStream_t st
   if (L.mode == 4) {
     auto kern = ratspn_leaf_kernel<KC, 4, KIND>;
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    kern<<<L.grid, 256, L.smem, st>>>(a);
+    if (a.redo) DPK_CUDA_TRY(launch_pdl(L.pdl, kern, L.grid, dim3(256), L.smem, st, a));
+    else kern<<<L.grid, 256, L.smem, st>>>(a);
   } else if (L.mode == 2) {
     auto kern = ratspn_leaf_kernel<KC, 2, KIND>;
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    kern<<<L.grid, 256, L.smem, st>>>(a);
+    if (a.redo) DPK_CUDA_TRY(launch_pdl(L.pdl, kern, L.grid, dim3(256), L.smem, st, a));
+    else kern<<<L.grid, 256, L.smem, st>>>(a);
   } else if (L.mode == 1) {
     auto kern = ratspn_leaf_kernel<KC, 1, KIND>;
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    kern<<<L.grid, 256, L.smem, st>>>(a);
+    if (a.redo) DPK_CUDA_TRY(launch_pdl(L.pdl, kern, L.grid, dim3(256), L.smem, st, a));
+    else kern<<<L.grid, 256, L.smem, st>>>(a);
   } else {
     ratspn_leaf_wide_kernel<KC, KIND><<<L.grid, 256, 0, st>>>(a);
   }
@@ -508,6 +514,7 @@ int ratspn_run_leaf(const dpk_ratspn_desc* d, const RatPlan& p, const float* x, 
   rsplit = (int)ceil_div(p.G0, a.regions_per_cta);
   L.grid = dim3((unsigned)((a.redo && L.mode != 0) ? std::min<int64_t>(ntiles, nsm) : ntiles), (unsigned)rsplit);
   L.smem = p.leaf_smem;
+  L.pdl = p.leaf_stream != 0;
   if (p.fwd_kind == DPK_LEAF_GAUSSIAN) return launch_leaf_kind<DPK_LEAF_GAUSSIAN>(p.kc.chunk, a, L, st);
   if (p.fwd_kind == kLeafGaussUnit) return launch_leaf_kind<kLeafGaussUnit>(p.kc.chunk, a, L, st);
   return launch_leaf_kind<DPK_LEAF_BERNOULLI>(p.kc.chunk, a, L, st);

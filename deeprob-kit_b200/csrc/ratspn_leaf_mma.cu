@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   // the Gaussian PREP launch and the main launch run GEMMs; the Bernoulli PREP launch only converts
   const bool tensor = !PREP || a.quad != 0;
 
+  pdl_launch_dependents();   // persistent, every CTA resident: the next launch may be staged behind this one (common.cuh)
   if (__ldg(a.wflag) != 0) {  // parameters outside the fp16 range: the exact kernel does everything
     if (PREP || CONV)
       for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.Bp / 32; i += (int64_t)gridDim.x * blockDim.x)

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kSThreads, 1) ratspn_leaf_stream_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bytes = (uint32_t)a.NT * 64u;
 
+  pdl_launch_dependents();   // persistent, every CTA resident: the next launch may be staged behind this one (common.cuh)
   if (__ldg(a.wflag) != 0) {   // parameters outside the fp16 range: the exact kernel does everything
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.Bp / 32; i += (int64_t)gridDim.x * blockDim.x) a.redo[i] = 1;
     return;

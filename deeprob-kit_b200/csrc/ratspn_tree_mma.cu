@@ -47,6 +47,7 @@ struct TreeArgs {
   const float* act0;            // element (column c, sample b) at (b >> 7) * act_ts + c * act_cs + (b & 127)  (RatPlan::act0_*)
   int64_t act_cs, act_ts;
   int tile_rows, c0_step;       // tile-major act[0]: (G0*KL, 0); column-major: (0, 128)
+  int pdl;                      // host only: stage this launch behind its predecessor (common.cuh)
   const unsigned char* wimg;    // [R][rep_bytes]
   float* part;                  // [R][C][Bp]
   const float* wlog[kTreeMaxD]; // log-softmax tables of the sum levels (exact path), [P][nOc][Kin2][OC]
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__((KL * O > 128 || O * O > 128) ? 256 : 512, 1) 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 8);
   const int warp = threadIdx.x >> 5;
   const int r = blockIdx.x;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1);
@@ -351,6 +353,9 @@ __global__ void __launch_bounds__((KL * O > 128 || O * O > 128) ? 256 : 512, 1) 
   const int t_first = blockIdx.y * a.G + c.wg, t_step = a.n_chunks * a.G;
   // rows of this repetition's leaf regions: region g, channel k -> row (g*KL + k), sample-minor
   const int row_base = (r << d) * KL;
+  // everything above (barriers, TMEM, the weight images, which an earlier launch wrote) may overlap the predecessor's tail;
+  // act[0], the flags and sqsum are its output
+  pdl_wait();
   if (c.warp_in_wg == 1 && t_first < a.n_tiles) tree_issue_pair<KL>(c, &tmap, t_first * a.c0_step, t_first * a.tile_rows + row_base);
   mbar_wait(wfull, 0u);
 
@@ -467,6 +472,7 @@ __global__ void ratspn_prep_tree_kernel(const float* __restrict__ wsoft, int P_t
 __global__ void tree_root_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int P, int C, int64_t B,
                                          int64_t Bp, const float* __restrict__ sqsum, const int* __restrict__ redo) {
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  pdl_wait();
   if (b >= B) return;
   const float add = (sqsum != nullptr && redo[b >> 5] == 0) ? sqsum[b] : 0.f;
   for (int c = 0; c < C; ++c) {
@@ -490,7 +496,7 @@ int launch_tree(const TreeArgs& a, const CUtensorMap& tmap, size_t smem, cudaStr
   auto kern = (a.depth <= 3) ? ratspn_tree_mma_kernel<KL, O, 3> : ratspn_tree_mma_kernel<KL, O, kTreeMaxD>;
   DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)a.R, (unsigned)a.n_chunks);
-  kern<<<grid, a.G * kTile, smem, st>>>(a, tmap);
+  DPK_CUDA_TRY(launch_pdl(a.pdl != 0, kern, grid, dim3((unsigned)(a.G * kTile)), smem, st, a, tmap));
   DPK_LAUNCH_CHECK("ratspn_tree_mma_kernel");
   return DPK_OK;
 }
@@ -525,6 +531,7 @@ int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
   TreeArgs a;
   a.act0 = ws + p.off_act[0];
   a.act_cs = p.act0_cs; a.act_ts = p.act0_ts; a.tile_rows = p.act0_tiled ? p.G0 * p.K : 0; a.c0_step = p.act0_tiled ? 0 : kTile;
+  a.pdl = p.leaf_stream;
   a.wimg = reinterpret_cast<const unsigned char*>(ws + p.off_timg);
   a.part = ws + p.off_rtmp;
   for (int e = 0; e < kTreeMaxD; ++e) a.wlog[e] = (e < p.n_sum) ? ws + p.off_wlog[e] : nullptr;
@@ -557,9 +564,10 @@ int ratspn_run_tree(const RatPlan& p, float* ws, float* out, cudaStream_t st) {
   }
   if (rc) return rc;
   ProfScope prof(CAT_ROOT, st);
-  tree_root_combine_kernel<<<(unsigned)ceil_div(p.B, 256), 256, 0, st>>>(
-      ws + p.off_rtmp, out, p.R, p.C, p.B, p.Bp, p.off_sqsum ? ws + p.off_sqsum : nullptr,
-      reinterpret_cast<const int*>(ws + p.off_mflags));
+  DPK_CUDA_TRY(launch_pdl(p.leaf_stream != 0, tree_root_combine_kernel, dim3((unsigned)ceil_div(p.B, 256)), dim3(256), 0, st,
+                          (const float*)(ws + p.off_rtmp), out, p.R, p.C, p.B, p.Bp,
+                          (const float*)(p.off_sqsum ? ws + p.off_sqsum : nullptr),
+                          reinterpret_cast<const int*>(ws + p.off_mflags)));
   DPK_LAUNCH_CHECK("tree_root_combine_kernel");
   return DPK_OK;
 }
