@@ -51,6 +51,7 @@ namespace {
 constexpr int kImg = kMmaTileN * kMmaKB * 2;  // 16 KB: [256 rows][64 B] fp16, 64B-swizzled, K-major
 constexpr int kStage = 4 * kImg;              // A hi | A lo | B hi | B lo
 constexpr int kThreads = 576;
+constexpr int kThreadsConv = 576 + 8 * 32;    // converting main launch: 8 more feeder warps (18-25) behind the epilogue warps
 constexpr int kEpiThread0 = 320;              // first epilogue thread (warp 10)
 constexpr uint32_t kSpinLimit = 1u << 20;     // bounded waits (a few seconds): a broken pipeline traps instead of hanging
 
@@ -187,7 +188,7 @@ constexpr int kSchedSlots = 8;   // unit ring: no role is ever more than 5 units
 // partition the features), so it factors out of all sum nodes and is added once to the final log-likelihood
 // (ratspn_tree_mma.cu) instead of per region here.
 template <bool PREP, bool GEN = false, bool CONV = false>
-__global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const LeafMmaArgs a) {
+__global__ void __launch_bounds__(CONV ? kThreadsConv : kThreads, 1) ratspn_leaf_mma_kernel(const LeafMmaArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;   // swizzled images need 1024-byte alignment
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMmaStages; ++s) { mbar_init(full + s, 9); mbar_init(empty + s, 1); }
+    for (int s = 0; s < kMmaStages; ++s) { mbar_init(full + s, CONV ? 17 : 9); mbar_init(empty + s, 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 8);
     for (int s = 0; s < kSchedSlots; ++s) { mbar_init(sfull + s, 1); mbar_init(sfree + s, 8); }
@@ -354,8 +355,8 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
       atomicAdd(st + 2, (unsigned long long)w_full);
       atomicAdd(st + 3, (unsigned long long)w_sched);
     }
-  } else if (warp < 10) {
-    // ---------------- operand feeders ----------------
+  } else if (warp < 10 || warp >= 18) {
+    // ---------------- operand feeders (warps 2-9; the converting launch adds warps 18-25) ----------------
     const int ft = threadIdx.x - 64;            // 0..255
     int stage = 0; uint32_t phase = 0;
     auto wait_empty = [&]() {
@@ -448,34 +449,36 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
           }
         }
       } else if constexpr (CONV) {
-        // Branch-free converter: 8 predicated 16-byte loads per K block (rows b0 + 4 i, features 4 c8 .. 4 c8 + 3 of
-        // the block), explicit byte addresses stepped by constants, two precomputed swizzled store offsets (rows
+        // Branch-free converter, 16 warps x 16 rows: 4 predicated 16-byte loads per thread and K block (rows b0 + 4 i,
+        // features 4 c8 .. 4 c8 + 3 of the block; with 8 warps x 8 loads the issuing warp waited 24 % of its time for
+        // `full` -- the conversion is a latency chain, twice the warps halve it), explicit byte addresses stepped by constants, two precomputed swizzled store offsets (rows
         // 4 i + rsub differ from row rsub by 256 i bytes, and in the swizzle term only through the parity of i).
-        const int cw = warp - 2;
+        constexpr int RPT = 4;                         // rows per thread
+        const int cw = warp < 10 ? warp - 2 : warp - 10;     // 0..15
         const int c8 = lane & 7, rsub = lane >> 3;
-        const int64_t b0 = (int64_t)m * kMmaTileM + cw * 32 + rsub;
+        const int64_t b0 = (int64_t)m * kMmaTileM + cw * 16 + rsub;
         // bits 0-7: row b0 + 4 i is inside the batch; bit 31: first N tile of this M tile (range check + sum of
         // squares happen there); bit 30: and the sum of squares is wanted.  One live register instead of three
         // (the flags were spilled to local memory otherwise: a long-scoreboard stall in every K block)
         uint32_t vmask = (j == 0 ? 0x80000000u : 0u) | ((j == 0 && a.sqsum != nullptr) ? 0x40000000u : 0u);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) vmask |= (b0 + 4 * i < a.B) ? (1u << i) : 0u;
+        for (int i = 0; i < RPT; ++i) vmask |= (b0 + 4 * i < a.B) ? (1u << i) : 0u;
 #define first ((vmask & 0x80000000u) != 0u)
 #define sqs ((vmask & 0x40000000u) != 0u)
         const char* xb = reinterpret_cast<const char*>(a.x) + ((size_t)b0 * a.lda + (size_t)c8 * 4) * 4;
         const size_t rstride = (size_t)a.lda * 16;     // four rows down, in bytes
-        const uint32_t row0 = cw * 32 + rsub;
+        const uint32_t row0 = cw * 16 + rsub;
         const uint32_t off_e = sw64_off(row0, c8 >> 1) + (c8 & 1) * 8;
         const uint32_t off_o = sw64_off(row0 + 4, c8 >> 1) + (c8 & 1) * 8 - 256;
-        float sqacc[8];
+        float sqacc[RPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sqacc[i] = 0.f;
+        for (int i = 0; i < RPT; ++i) sqacc[i] = 0.f;
         uint32_t umax = 0;                              // running max of |x| as ordered bits (NaN / inf sort above every finite value)
-        auto load = [&](int kb, float4 (&v)[8]) {
+        auto load = [&](int kb, float4 (&v)[RPT]) {
           const bool fok = kb * kMmaKB + c8 * 4 < a.D;
           const char* p = xb + (size_t)kb * (kMmaKB * 4);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < RPT; ++i) {
             const uint32_t pred = (fok && ((vmask >> i) & 1u)) ? 1u : 0u;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
                          "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
@@ -484,11 +487,11 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
                          : "l"(p + (size_t)i * rstride), "r"(pred));
           }
         };
-        auto convert = [&](float4 (&buf)[8]) {
+        auto convert = [&](float4 (&buf)[RPT]) {
           wait_empty();
           unsigned char* A = sm + stage * kStage;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < RPT; ++i) {
             const float4 v = buf[i];
             if (first) {
               umax = max(umax, max(max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu),
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
           publish();
         };
         // two register sets, loads two K blocks ahead of their use (no register copies: a copy would wait for the load)
-        float4 bufA[8], bufB[8];
+        float4 bufA[RPT], bufB[RPT];
         load(kb0, bufA);
         if (kb0 + 1 < kb1) load(kb0 + 1, bufB);
         for (int kb = kb0; kb < kb1; kb += 2) {
@@ -520,11 +523,11 @@ __global__ void __launch_bounds__(kThreads, 1) ratspn_leaf_mma_kernel(const Leaf
           }
         }
         if (first) {
-          // all 8 rows of a thread lie in one 32-sample group (rows cw*32 .. cw*32 + 31)
+          // all rows of a thread lie in one 32-sample group (rows cw*16 .. cw*16 + 15)
           if (umax > __float_as_uint(a.xlimit)) a.redo[b0 >> 5] = 1;
           if (sqs) {   // the 8 lanes of a row group hold the 8 four-feature columns of their rows
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < RPT; ++i) {
               float v = sqacc[i];
               v += __shfl_xor_sync(0xffffffffu, v, 1);
               v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -1083,7 +1086,7 @@ int ratspn_run_leaf_mma(const RatPlan& p, const float* x, float* ws, cudaStream_
     a.xlimit = 30000.f;
     DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(CAT_LEAF_MMA, st);
-    ratspn_leaf_mma_kernel<false, false, true><<<grid_main, kThreads, smem, st>>>(a);
+    ratspn_leaf_mma_kernel<false, false, true><<<grid_main, kThreadsConv, smem, st>>>(a);
     DPK_LAUNCH_CHECK("ratspn_leaf_mma_kernel<conv>");
   } else {
   DPK_CUDA_TRY(cudaFuncSetAttribute(ratspn_leaf_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
