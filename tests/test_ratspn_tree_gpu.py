@@ -128,3 +128,25 @@ def test_bench_batch_against_oracle():
     assert rel_err(part, out[20000:28192 + 20000]) < 1e-6
     perm = torch.randperm(65536, device=DEV)
     assert rel_err(model(x[perm]), out[perm]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["t_k8", "gauss784"])
+def test_unaligned_input_takes_the_exact_leaf_path(name, tree_on, monkeypatch):
+    """x whose storage starts 4 bytes off a 16-byte boundary cannot feed the tensor-core leaf kernels (16-byte loads,
+    TMA): the exact kernel computes the whole leaf level -- quadratic term included, so the root must not add the
+    per-sample -x^2/2 again -- and the fused tree kernel runs behind it.  Same values as for the aligned copy."""
+    monkeypatch.setenv("DPK_LEAF_MMA", "1")
+    cfg = CASES[name]
+    model = product_model(cfg, DEV, scale_grad=False)
+    x, _ = pg.ratspn_inputs(cfg)
+    flat = torch.empty(x.numel() + 1, device=DEV)
+    xu = flat[1:].view_as(x)
+    xu.copy_(x)
+    assert xu.data_ptr() % 16 == 4 and xu.is_contiguous()
+    out_u = model(xu)
+    out_a = model(x.to(DEV))
+    assert rel_err(out_u, out_a) < 2e-6
+    for leaf_stream in ("1",):
+        monkeypatch.setenv("DPK_LEAF_STREAM", leaf_stream)
+        if cfg["rg_repetitions"] * cfg["rg_batch"] * (1 << cfg["rg_depth"]) <= 256:
+            assert rel_err(model(xu), out_a) < 2e-6
