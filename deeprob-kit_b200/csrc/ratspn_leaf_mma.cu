@@ -679,24 +679,41 @@ __global__ void __launch_bounds__(CONV ? kThreadsConv : kThreads, 1) ratspn_leaf
                 if (i < nvalid) atomicAdd(op + i, __uint_as_float(v[i]) * osc);
             }
           } else if (a.linear) {
-            // generic layer: row-major output, this thread owns 32 consecutive columns of its row
-            if (b < a.B) {
+            // generic layer: row-major output, this thread holds 32 consecutive columns of its row
+            float r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              r[i] = fmaf(__uint_as_float(v[i]), osc, cst_s[col0 + i]);
+              if (a.relu) r[i] = fmaxf(r[i], 0.f);
+            }
+            if (nvalid == 32 && (a.Ntot & 3) == 0) {
+              // Through the warp's 2 KB of staging (the x^2 block of the leaf role, unused here): 16 columns at a time,
+              // swizzled at 16-byte granularity, so that a store instruction writes 8 rows x 64 contiguous bytes (full
+              // sectors) instead of 32 rows x 16 bytes -- the drain of these GEMMs was bound by the half-sector writes.
+              const int64_t row0 = (int64_t)m * kMmaTileM + h * 128 + q * 32;
+              const uint32_t ws = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                __syncwarp();
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                  *reinterpret_cast<float4*>(sqw + lane * 16 + (((uint32_t)c4 ^ ws) << 2)) =
+                      make_float4(r[half * 16 + 4 * c4], r[half * 16 + 4 * c4 + 1], r[half * 16 + 4 * c4 + 2], r[half * 16 + 4 * c4 + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int rr = k * 8 + (lane >> 2), c4 = lane & 3;
+                  const float4 o = *reinterpret_cast<const float4*>(sqw + rr * 16 + (((uint32_t)c4 ^ (((uint32_t)rr >> 1) & 3u)) << 2));
+                  if (row0 + rr < a.B)
+                    *reinterpret_cast<float4*>(a.out + (size_t)(row0 + rr) * a.Ntot + col_base + col0 + half * 16 + c4 * 4) = o;
+                }
+              }
+              __syncwarp();
+            } else if (b < a.B) {
               float* op = a.out + (size_t)b * a.Ntot + col_base + col0;
-              float r[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                r[i] = fmaf(__uint_as_float(v[i]), osc, cst_s[col0 + i]);
-                if (a.relu) r[i] = fmaxf(r[i], 0.f);
-              }
-              if (nvalid == 32 && (a.Ntot & 3) == 0) {
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4)
-                  reinterpret_cast<float4*>(op)[i4] = make_float4(r[4 * i4], r[4 * i4 + 1], r[4 * i4 + 2], r[4 * i4 + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < nvalid) op[i] = r[i];
-              }
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) op[i] = r[i];
             }
           } else if (nvalid == 32 && bok && !wide) {
             float* op = a.out + (b >> 7) * a.out_ts + (size_t)(col_base + col0) * a.out_cs + (b & 127);
