@@ -674,9 +674,17 @@ __global__ void __launch_bounds__(CONV ? kThreadsConv : kThreads, 1) ratspn_leaf
             // split-K partial sums: accumulate into the row-major result
             if (b < a.B) {
               float* op = a.out + (size_t)b * a.Ntot + col_base + col0;
+              if (nvalid == 32 && (a.Ntot & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nvalid) atomicAdd(op + i, __uint_as_float(v[i]) * osc);
+                for (int i4 = 0; i4 < 8; ++i4)      // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the instructions
+                  atomicAdd(reinterpret_cast<float4*>(op) + i4,
+                            make_float4(__uint_as_float(v[4 * i4]) * osc, __uint_as_float(v[4 * i4 + 1]) * osc,
+                                        __uint_as_float(v[4 * i4 + 2]) * osc, __uint_as_float(v[4 * i4 + 3]) * osc));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < nvalid) atomicAdd(op + i, __uint_as_float(v[i]) * osc);
+              }
             }
           } else if (a.linear) {
             // generic layer: row-major output, this thread holds 32 consecutive columns of its row
