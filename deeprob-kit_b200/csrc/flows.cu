@@ -202,6 +202,7 @@ __global__ void feature_reduce_kernel(const float* __restrict__ x, const float* 
     if (f >= F) return;
     const float c = center ? center[f] : 0.f;
     float s = 0.f, d = 0.f;
+#pragma unroll 8
     for (int64_t b = b0; b < b1; ++b) {
       const float xv = x[b * F + f];
       if (mode == 0) s += xv;
@@ -240,6 +241,30 @@ __global__ void feature_affine_kernel(const float* __restrict__ x, const float* 
     float v = fmaf(x[idx], __ldg(a + f), __ldg(c + f));
     if (y) v = fmaf(__ldg(k + f), y[idx] - __ldg(mu + f), v);
     out[idx] = v;
+  }
+}
+
+// the same for (B, F) tensors with F % 4 == 0: 16-byte accesses, no division per element (the per-feature vectors are
+// read as float4 from L1/L2; a thread's feature offset advances by a constant)
+__global__ void __launch_bounds__(256) feature_affine_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ a,
+                                                                 const float4* __restrict__ c, const float4* __restrict__ y,
+                                                                 const float4* __restrict__ k, const float4* __restrict__ mu,
+                                                                 float4* __restrict__ out, int64_t total4, int F4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int f = (int)(idx % F4);
+  const int fstep = (int)(stride % F4);
+  for (; idx < total4; idx += stride) {
+    const float4 xv = __ldcs(x + idx), av = __ldg(a + f), cv = __ldg(c + f);
+    float4 v = make_float4(fmaf(xv.x, av.x, cv.x), fmaf(xv.y, av.y, cv.y), fmaf(xv.z, av.z, cv.z), fmaf(xv.w, av.w, cv.w));
+    if (y) {
+      const float4 yv = __ldcs(y + idx), kv = __ldg(k + f), mv = __ldg(mu + f);
+      v.x = fmaf(kv.x, yv.x - mv.x, v.x); v.y = fmaf(kv.y, yv.y - mv.y, v.y);
+      v.z = fmaf(kv.z, yv.z - mv.z, v.z); v.w = fmaf(kv.w, yv.w - mv.w, v.w);
+    }
+    __stcs(out + idx, v);
+    f += fstep;
+    if (f >= F4) f -= F4;
   }
 }
 
@@ -452,7 +477,15 @@ extern "C" int dpk_feature_affine(const float* x, const float* a, const float* c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t total = batch * features * inner;
   ProfScope prof(y ? CAT_FLOW_BWD : CAT_FLOW, st);
-  feature_affine_kernel<<<flat_grid(total), 256, 0, st>>>(x, a, c, y, k, mu, out, total, features, inner);
+  auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (inner == 1 && features % 4 == 0 && al16(x) && al16(a) && al16(c) && al16(y) && al16(k) && al16(mu) && al16(out)) {
+    feature_affine_vec_kernel<<<flat_grid(total / 4), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(c),
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(k), reinterpret_cast<const float4*>(mu),
+        reinterpret_cast<float4*>(out), total / 4, features / 4);
+  } else {
+    feature_affine_kernel<<<flat_grid(total), 256, 0, st>>>(x, a, c, y, k, mu, out, total, features, inner);
+  }
   DPK_LAUNCH_CHECK("feature_affine_kernel");
   return DPK_OK;
 }
