@@ -879,6 +879,85 @@ __global__ void __launch_bounds__(128) dgc_sum_bwd_fast_kernel(const float* __re
   }
 }
 
+
+// More than OC x IC channels (the 16 / 32-channel layers of the MNIST-example model): the same factorised, prefetching
+// loop per (input chunk = blockIdx.z, output chunk) block.  x of the chunk is re-read once per output chunk and d/dx is
+// accumulated across output chunks by the owning thread (read-modify-write of its own element), all mostly out of L2:
+// 2.5 TB/s of DRAM traffic against 0.29 for the one-sample-at-a-time kernel below.  The shift m is the chunk's own maximum:
+// any finite shift factorises exactly, and y_o >= x_i + log w_oi bounds m - y_o from above.
+template <int OC, int IC>
+__global__ void __launch_bounds__(128) dgc_sum_bwd_chunk_kernel(const float* __restrict__ x, const float* __restrict__ wsoft,
+                                                                const float* __restrict__ y, const float* __restrict__ g,
+                                                                float* __restrict__ gx, float* __restrict__ nstat, int64_t B,
+                                                                int I, int O, int HW, int64_t per_slice) {
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hw >= HW) return;
+  const int i0 = blockIdx.z * IC;
+  const int64_t b0 = blockIdx.y * per_slice, b1 = min((long long)B, (long long)(b0 + per_slice));
+  if (b0 >= b1) return;
+  const size_t sx = (size_t)I * HW, so = (size_t)O * HW;
+  for (int o0 = 0; o0 < O; o0 += OC) {
+    float w[OC][IC], n[OC][IC];
+#pragma unroll
+    for (int o = 0; o < OC; ++o)
+#pragma unroll
+      for (int i = 0; i < IC; ++i) {
+        w[o][i] = (o0 + o < O && i0 + i < I) ? __ldg(wsoft + ((size_t)(o0 + o) * I + i0 + i) * HW + hw) : 0.f;
+        n[o][i] = 0.f;
+      }
+    const float* xp = x + b0 * sx + (size_t)i0 * HW + hw;
+    const float* yp = y + b0 * so + (size_t)o0 * HW + hw;
+    const float* gp = g + b0 * so + (size_t)o0 * HW + hw;
+    float* gxp = gx ? gx + b0 * sx + (size_t)i0 * HW + hw : nullptr;
+    float xn[IC], yn[OC], gn[OC], on[IC];
+    auto load = [&](const float* xq, const float* yq, const float* gq, const float* oq) {
+#pragma unroll
+      for (int i = 0; i < IC; ++i) {
+        xn[i] = (i0 + i < I) ? __ldg(xq + (size_t)i * HW) : -INFINITY;
+        on[i] = (oq != nullptr && o0 > 0 && i0 + i < I) ? __ldcg(oq + (size_t)i * HW) : 0.f;   // d/dx so far
+      }
+#pragma unroll
+      for (int o = 0; o < OC; ++o) {
+        gn[o] = (o0 + o < O) ? __ldg(gq + (size_t)o * HW) : 0.f;
+        yn[o] = (o0 + o < O) ? __ldg(yq + (size_t)o * HW) : 0.f;
+      }
+    };
+    load(xp, yp, gp, gxp);
+    for (int64_t b = b0; b < b1; ++b) {
+      float xv[IC], f[OC], ov[IC];
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < IC; ++i) { xv[i] = xn[i]; ov[i] = on[i]; m = fmaxf(m, xv[i]); }
+      if (!(fabsf(m) <= FLT_MAX)) m = 0.f;
+#pragma unroll
+      for (int o = 0; o < OC; ++o) f[o] = (gn[o] != 0.f && fabsf(yn[o]) <= FLT_MAX) ? gn[o] * __expf(fminf(m - yn[o], 80.f)) : 0.f;
+      float* gcur = gxp;
+      xp += sx; yp += so; gp += so;
+      if (gxp) gxp += sx;
+      if (b + 1 < b1) load(xp, yp, gp, gxp);
+#pragma unroll
+      for (int i = 0; i < IC; ++i) {
+        const float e = __expf(fminf(xv[i] - m, 80.f));
+        float acc = ov[i];
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+          const float post = w[o][i] * (e * f[o]);
+          n[o][i] += post;
+          acc += post;
+        }
+        if (gcur && i0 + i < I) gcur[(size_t)i * HW] = acc;
+      }
+    }
+    if (nstat) {
+#pragma unroll
+      for (int o = 0; o < OC; ++o)
+#pragma unroll
+        for (int i = 0; i < IC; ++i)
+          if (o0 + o < O && i0 + i < I && n[o][i] != 0.f) atomicAdd(nstat + ((size_t)(o0 + o) * I + i0 + i) * HW + hw, n[o][i]);
+    }
+  }
+}
+
 // grad_raw[o,i,hw] += N - softmax * sum_i N
 __global__ void dgc_sum_finalize_kernel(const float* __restrict__ wsoft, const float* __restrict__ nstat,
                                         float* __restrict__ gw, int O, int I, int HW) {
@@ -1253,6 +1332,11 @@ extern "C" int dpk_dgc_sum_backward(const float* x, const float* weight, const f
       dgc_sum_bwd_fast_kernel<4, 4, false><<<grid2, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per2, ProdDesc{});
     else
       dgc_sum_bwd_fast_kernel<8, 8, false><<<grid2, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per2, ProdDesc{});
+  } else if (fast) {
+    const int64_t nz = ceil_div(in_channels, 8);
+    const int64_t per2 = std::max<int64_t>(16, ceil_div(batch, std::max<int64_t>(1, ceil_div((int64_t)12 * sm_count(), bx * nz))));
+    dgc_sum_bwd_chunk_kernel<8, 8><<<dim3((unsigned)bx, (unsigned)ceil_div(batch, per2), (unsigned)nz), 128, 0, st>>>(
+        x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per2);
   } else if (out_channels <= 4 && in_channels <= 4)
     dgc_sum_bwd_kernel<4, 4><<<grid, 128, 0, st>>>(x, wsoft, out, grad_out, grad_x, ns, batch, in_channels, out_channels, hw, per);
   else if (out_channels <= 4)
